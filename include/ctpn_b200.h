@@ -1,0 +1,147 @@
+/*
+ * ctpn_b200 -- C ABI of the B200-native CTPN detection hot path.
+ *
+ * One shared library (libctpn_b200.so, nvcc -gencode arch=compute_100a,code=sm_100a),
+ * plain pointers and sizes only, no torch / C++ types.  Every entry point returns an
+ * int status (0 = success); ctpn_last_error() gives the message for the calling thread.
+ * Unless a name ends in _host, pointers are DEVICE pointers on the current device and
+ * `stream` is a cudaStream_t passed as void*.  No entry point allocates device memory
+ * except ctpn_nms_host (grow-only per-device scratch) and ctpn_net_* weight storage.
+ *
+ * Reference interfaces replaced (paths relative to eragonruan/text-detection-ctpn @ c04a571e):
+ *   ctpn_nms_host        lib/utils/gpu_nms.hpp:1-2  `void _nms(int*,int*,const float*,int,int,float,int)`
+ *                        (called by lib/utils/gpu_nms.pyx:31)
+ *   ctpn_nms_sorted      lib/utils/nms_kernel.cu:34-78 (nms_kernel) + :124-139 (host greedy scan)
+ *   ctpn_proposals       lib/rpn_msr/proposal_layer_tf.py:14-157 (tf.py_func body, lib/networks/network.py:214)
+ *   ctpn_conv1_1 / ctpn_conv3x3 / ctpn_maxpool2x2
+ *                        lib/networks/network.py:160-183 (conv), :189-196 (max_pool)
+ *   ctpn_bilstm_recurrent, ctpn_gemm_planes
+ *                        lib/networks/network.py:88-113 (Bilstm), :144-158 (lstm_fc)
+ *   ctpn_net_forward     lib/networks/VGGnet_test.py:16-52 up to the two head tensors
+ *                        (the demo_pb.py:73-75 boundary), fed by lib/fast_rcnn/test.py:7-31
+ */
+#ifndef CTPN_B200_H_
+#define CTPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTPN_OK 0
+#define CTPN_ERR_INVALID 1   /* bad argument */
+#define CTPN_ERR_CUDA 2      /* CUDA runtime / driver error */
+#define CTPN_ERR_WORKSPACE 3 /* workspace too small */
+#define CTPN_ERR_NO_DEVICE 4 /* no usable sm_100 device */
+
+/* ---- library ------------------------------------------------------------------------- */
+int ctpn_version(void);                 /* 10000*major + 100*minor + patch */
+const char *ctpn_last_error(void);      /* thread-local, never NULL */
+int ctpn_device_ok(int device_id);      /* CTPN_OK iff device exists and is compute capability 10.x */
+
+/* Per-launch timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * numbers).  ctpn_prof_enable(1) clears and starts recording, (0) stops.  ctpn_prof_report
+ * synchronises the recorded events and writes a JSON array
+ *   [{"kernel": label, "launches": n, "ms": total, "work": algorithmic FLOPs}, ...]
+ * into buf (if capacity allows); *needed receives the required size including the NUL. */
+int ctpn_prof_enable(int on);
+int ctpn_prof_report(char *buf, size_t capacity, size_t *needed);
+
+/* ---- NMS ------------------------------------------------------------------------------
+ * ctpn_nms_host: drop-in for `_nms`.  All pointers are HOST memory.  boxes_host is row
+ * major [boxes_num, boxes_dim] (boxes_dim >= 4, columns x1,y1,x2,y2,...), already sorted by
+ * score descending.  keep_out must hold boxes_num ints; *num_out receives the count.
+ * Suppression rule: IoU(+1 pixel convention, float32, no FMA contraction) > thresh.
+ * Unlike `_nms` it returns a status instead of printing CUDA errors and carrying on. */
+int ctpn_nms_host(int *keep_out, int *num_out, const float *boxes_host, int boxes_num,
+                  int boxes_dim, float nms_overlap_thresh, int device_id);
+
+/* Batched device NMS over pre-sorted boxes.  boxes: [batch][max_n][4] float; counts[batch]
+ * gives the valid prefix of each image.  keep_out: [batch][max_keep] positions (ascending),
+ * num_out[batch].  max_keep > 0 stops the greedy scan early (proposal_layer_tf.py:145-146). */
+size_t ctpn_nms_workspace_bytes(int batch, int max_n);
+int ctpn_nms_sorted(const float *boxes, const int *counts, int batch, int max_n, float thresh,
+                    int max_keep, int *keep_out, int *num_out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* ---- proposal layer (batched; per-image semantics == the reference's batch-1 layer) ---
+ * cls:  [batch][H][W][20]  softmax probabilities (cls_is_logit=0, the demo_pb.py boundary)
+ *                          or raw rpn_cls_score logits (cls_is_logit=1; pair softmax fused)
+ * bbox: [batch][H][W][40]  (dx,dy,dw,dh) per anchor
+ * im_info: [batch][3]      (blob_h, blob_w, im_scale)
+ * rois_out:  [batch][post_nms_topN][5] = (score,x1,y1,x2,y2), rows past the count are 0
+ * index_out: [batch][post_nms_topN]    flat (h,w,a) anchor index of each row (may be NULL)
+ * count_out: [batch]
+ * anchors_py2 != 0 selects the Python-2 anchor table. */
+size_t ctpn_proposals_workspace_bytes(int batch, int H, int W, int pre_nms_topN);
+int ctpn_proposals(const float *cls, int cls_is_logit, const float *bbox, const float *im_info,
+                   int batch, int H, int W, int feat_stride, int pre_nms_topN, int post_nms_topN,
+                   float nms_thresh, float min_size, int anchors_py2, float *rois_out,
+                   int *index_out, int *count_out, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* ---- network stages --------------------------------------------------------------------
+ * Activation format ("planes"): P in {1,2,3} bf16 tensors [P][B][H][W][C] whose element-wise
+ * sum is the float32 value (a = a1 + a2 (+ a3), a1 = bf16(a), a2 = bf16(a - a1), ...).
+ * P=1 is plain bf16, P=3 carries all 24 mantissa bits.  Products of planes are accumulated
+ * in float32 on the tensor cores (tcgen05, TMEM accumulators).
+ * Weight format: bf16 [P][Cout][taps][Cin] (K-major), made by ctpn_pack_weights from the
+ * TF layout [taps][Cin][Cout] (HWIO for 3x3, [K][N] for matmuls). */
+int ctpn_pack_weights(const float *w_tf, int taps, int cin, int cout, int cout_pad, int planes,
+                      void *w_planes_out, void *stream);
+
+/* conv1_1: uint8 BGR image [B][H][W][3] (or float32 blob when src_is_f32) -> 64-channel planes,
+ * float32 direct convolution; fuses the mean subtraction of lib/fast_rcnn/test.py:9
+ * (lut[256][3] = float32(double(v) - PIXEL_MEANS[c])), bias and ReLU. */
+int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, const float *w_hwio,
+                 const float *bias, void *out_planes, int B, int H, int W, int planes, void *stream);
+
+/* 3x3 SAME conv (taps=9) or 1x1 / matmul (taps=1) on planes with tcgen05 tensor cores.
+ * flags: bit0 ReLU, bit1 fused 2x2/2 VALID max-pool (taps=9 only), bit2 float32 output
+ * [B][H][W][Cout] instead of planes.  Cin % 64 == 0, Cout % 64 == 0. */
+#define CTPN_F_RELU 1
+#define CTPN_F_POOL 2
+#define CTPN_F_OUT_F32 4
+int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B,
+                 int H, int W, int cin, int cout, int taps, int planes, int flags, void *stream);
+/* Same contract, float32 SIMT implementation (no tensor cores): kernel-level reference used
+ * by the tests and by CTPN_CONV_IMPL=simt. */
+int ctpn_conv3x3_simt(const void *in_planes, const void *w_planes, const float *bias, void *out,
+                      int B, int H, int W, int cin, int cout, int taps, int planes, int flags,
+                      void *stream);
+
+/* BiLSTM recurrence (network.py:97-101).  xproj: float32 [R][W][1024] = x.Wx + b for
+ * (fw gates i,j,f,o | bw gates i,j,f,o); wh_fw / wh_bw: float32 [128][512] recurrent kernels
+ * (rows 512..639 of the TF kernel).  Output planes [P][R][W][256] = concat(h_fw, h_bw). */
+int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, const float *wh_bw,
+                          void *out_planes, int R, int W, int planes, void *stream);
+
+/* ---- whole network up to the head tensors -------------------------------------------- */
+typedef struct ctpn_net ctpn_net_t;
+int ctpn_net_create(ctpn_net_t **net, int planes);
+int ctpn_net_destroy(ctpn_net_t *net);
+/* options: "keep_activations" (1: every layer gets its own workspace region so that
+ * ctpn_net_debug_tap can read all of them after a forward), "conv_simt" (1: run the float32 SIMT
+ * reference kernels instead of the tcgen05 path). */
+int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value);
+/* name = TF variable name; data = host float32 in TF layout. */
+int ctpn_net_set_weight(ctpn_net_t *net, const char *name, const float *data_host, size_t count);
+size_t ctpn_net_workspace_bytes(const ctpn_net_t *net, int B, int H, int W);
+/* images: uint8 [B][H][W][3] BGR (device).  Outputs (device, float32):
+ * cls_score [B][H/16][W/16][20] logits, bbox_pred [B][H/16][W/16][40]. */
+int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_f32, int B, int H, int W,
+                     float *cls_score_out, float *bbox_pred_out, void *workspace,
+                     size_t workspace_bytes, void *stream);
+/* feature-map size after the four VALID pools */
+int ctpn_net_feature_hw(int H, int W, int *fh, int *fw);
+/* Debug tap: copies the most recent forward's named activation ("conv1_1" ... "rpn_conv/3x3",
+ * "lstm_out", "lstm_o") to out_f32 (device float32, NHWC).  Returns element count via *count. */
+int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_f32, size_t capacity,
+                       size_t *count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTPN_B200_H_ */

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Stand-alone GPU checks, run as subprocesses by the -m gpu tests so that a faulting kernel
+(device trap, launch failure) cannot poison the pytest process.  Each sub-command prints one
+JSON line {"ok": bool, ...} as its last line of stdout.
+
+    python tests/gpu_checks.py conv --B 2 --H 37 --W 56 --cin 128 --cout 128 --taps 9 --planes 2 --flags 1
+    python tests/gpu_checks.py bilstm --R 37 --W 56 --planes 2
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "text-detection-ctpn_b200"))
+
+F_RELU, F_POOL, F_F32 = 1, 2, 4
+
+
+def split_planes_t(x, planes):
+    """float32 tensor -> [P, ...] bf16 planes with x ~= sum(planes) (same rule as the kernels)."""
+    import torch
+    out, r = [], x.clone()
+    for _ in range(planes):
+        h = r.to(torch.bfloat16)
+        out.append(h)
+        r = r - h.to(torch.float32)
+    return torch.stack(out, 0)
+
+
+def cmd_conv(a):
+    import torch
+    from ctpn_b200 import _native as N
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(a.seed)
+    x = torch.randn(a.B, a.H, a.W, a.cin, generator=g)
+    x = torch.relu(x) if a.nonneg else x
+    w = torch.randn(a.taps, a.cin, a.cout, generator=g) * (2.0 / (a.taps * a.cin)) ** 0.5
+    b = torch.randn(a.cout, generator=g) * 0.1
+    xp = split_planes_t(x.to(dev), a.planes).contiguous()                       # [P,B,H,W,C]
+    wp_dev = torch.empty(a.planes * a.cout * a.taps * a.cin, dtype=torch.bfloat16, device=dev)
+    w_dev, b_dev = w.to(dev).contiguous(), b.to(dev).contiguous()
+    N.check(N.lib.ctpn_pack_weights(N.ptr(w_dev), a.taps, a.cin, a.cout, a.cout, a.planes, N.ptr(wp_dev), N.stream_ptr()), "pack")
+    pool = bool(a.flags & F_POOL)
+    Ho, Wo = (a.H // 2, a.W // 2) if pool else (a.H, a.W)
+    if a.flags & F_F32:
+        out = torch.full((a.B, Ho, Wo, a.cout), float("nan"), dtype=torch.float32, device=dev)
+    else:
+        out = torch.zeros((a.planes, a.B, Ho, Wo, a.cout), dtype=torch.bfloat16, device=dev)
+    fn = N.lib.ctpn_conv3x3_simt if a.impl == "simt" else N.lib.ctpn_conv3x3
+    N.check(fn(N.ptr(xp), N.ptr(wp_dev), N.ptr(b_dev), N.ptr(out), a.B, a.H, a.W, a.cin, a.cout, a.taps, a.planes,
+               a.flags, N.stream_ptr()), "conv")
+    torch.cuda.synchronize()
+    got = out.double() if a.flags & F_F32 else out.double().sum(0)
+    # reference: float64 conv on the exact values the planes carry
+    xr = xp.double().sum(0).permute(0, 3, 1, 2)
+    wr = wp_dev.view(a.planes, a.cout, a.taps, a.cin).double().sum(0)          # [Cout, taps, Cin]
+    k = 3 if a.taps == 9 else 1
+    wr = wr.view(a.cout, k, k, a.cin).permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(xr, wr, b_dev.double(), padding=k // 2)
+    if a.flags & F_RELU:
+        y = torch.relu(y)
+    if pool:
+        y = torch.nn.functional.max_pool2d(y, 2, 2)
+    y = y.permute(0, 2, 3, 1)
+    err = (got - y).abs()
+    scale = y.abs().max().item()
+    max_err = err.max().item()
+    nan = int(torch.isnan(got).sum().item())
+    tol = {1: 6e-3, 2: 4e-5, 3: 5e-6}[a.planes] if not (a.flags & F_F32) else {1: 2e-5, 2: 2e-5, 3: 5e-6}[a.planes]
+    ok = nan == 0 and max_err <= tol * max(scale, 1e-6)
+    res = dict(ok=bool(ok), max_err=max_err, scale=scale, rel=max_err / max(scale, 1e-30), tol=tol, nan=nan)
+    if not ok:
+        idx = torch.nonzero(err > tol * scale)[:8].tolist()
+        res["first_bad"] = idx
+        res["bad_frac"] = float((err > tol * scale).double().mean().item())
+        res["got"] = [got[tuple(i)].item() for i in idx]
+        res["want"] = [y[tuple(i)].item() for i in idx]
+    print(json.dumps(res))
+    return 0 if ok else 1
+
+
+def cmd_bilstm(a):
+    import torch
+    from ctpn_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    rs = np.random.RandomState(a.seed)
+    xproj = (rs.standard_normal((a.R, a.W, 1024)) * 1.0).astype(np.float32)
+    wh = [(rs.uniform(-0.07, 0.07, (128, 512))).astype(np.float32) for _ in range(2)]
+    xd = torch.from_numpy(xproj).to(dev)
+    whd = [torch.from_numpy(w).to(dev) for w in wh]
+    out = torch.zeros((a.planes, a.R, a.W, 256), dtype=torch.bfloat16, device=dev)
+    N.check(N.lib.ctpn_bilstm_recurrent(N.ptr(xd), N.ptr(whd[0]), N.ptr(whd[1]), N.ptr(out), a.R, a.W, a.planes, N.stream_ptr()), "bilstm")
+    torch.cuda.synchronize()
+    got = out.double().sum(0).cpu().numpy()
+    # float64 reference of the TF 1.3 LSTMCell recurrence (oracle.net_cpu.lstm_dir without the x-projection)
+    ref = np.zeros((a.R, a.W, 256))
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    for d in range(2):
+        h = np.zeros((a.R, 128)); c = np.zeros((a.R, 128))
+        steps = range(a.W - 1, -1, -1) if d else range(a.W)
+        for t in steps:
+            gt = xproj[:, t, d * 512:(d + 1) * 512].astype(np.float64) + h @ wh[d].astype(np.float64)
+            i, j, f, o = gt[:, :128], gt[:, 128:256], gt[:, 256:384], gt[:, 384:]
+            c = sig(f + 1.0) * c + sig(i) * np.tanh(j)
+            h = sig(o) * np.tanh(c)
+            ref[:, t, d * 128:(d + 1) * 128] = h
+    max_err = float(np.abs(got - ref).max())
+    tol = {1: 4e-3, 2: 2e-5, 3: 5e-6}[a.planes]
+    ok = bool(np.isfinite(got).all() and max_err <= tol)
+    print(json.dumps(dict(ok=ok, max_err=max_err, tol=tol)))
+    return 0 if ok else 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    c = sub.add_parser("conv")
+    for k, d in dict(B=1, H=8, W=16, cin=64, cout=64, taps=9, planes=1, flags=0, seed=0, nonneg=0).items():
+        c.add_argument("--" + k, type=int, default=d)
+    c.add_argument("--impl", default="tc")
+    l = sub.add_parser("bilstm")
+    for k, d in dict(R=37, W=56, planes=2, seed=0).items():
+        l.add_argument("--" + k, type=int, default=d)
+    a = ap.parse_args()
+    return {"conv": cmd_conv, "bilstm": cmd_bilstm}[a.cmd](a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,49 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol the header declares;
+the ctypes table in ctpn_b200/_native.py covers exactly the header."""
+import os
+import re
+
+from ctpn_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ctpn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctpn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(N.lib, n), "libctpn_b200.so does not export %s" % n
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(N.SIGNATURES) == header_functions()
+
+
+def test_version_and_error_string():
+    assert N.lib.ctpn_version() >= 100
+    assert isinstance(N.last_error(), str)
+
+
+def test_invalid_arguments_are_reported_not_crashed():
+    # argument validation happens before any CUDA call, so this works without a GPU
+    import ctypes as C
+    num = C.c_int(-1)
+    rc = N.lib.ctpn_nms_host(None, C.byref(num), None, 5, 5, 0.7, 0)
+    assert rc == 1 and "null" in N.last_error()
+    keep = (C.c_int * 4)()
+    rc = N.lib.ctpn_nms_host(keep, C.byref(num), None, 0, 5, 0.7, 0)      # empty input: OK, zero kept
+    assert rc == 0 and num.value == 0
+    boxes = (C.c_float * 12)()
+    rc = N.lib.ctpn_nms_host(keep, C.byref(num), boxes, 4, 3, 0.7, 0)
+    assert rc == 1 and "boxes_dim" in N.last_error()
+    fh, fw = C.c_int(), C.c_int()
+    assert N.lib.ctpn_net_feature_hw(600, 900, C.byref(fh), C.byref(fw)) == 0 and (fh.value, fw.value) == (37, 56)
+    assert N.lib.ctpn_net_feature_hw(1200, 1600, C.byref(fh), C.byref(fw)) == 0 and (fh.value, fw.value) == (75, 100)
+    assert N.lib.ctpn_conv3x3(None, None, None, None, 1, 8, 8, 64, 64, 9, 1, 0, None) == 1
+    assert N.lib.ctpn_nms_workspace_bytes(1, 12000) == 12000 * 188 * 8

@@ -1,0 +1,68 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (ctpn_conv3x3) and the float32 SIMT reference
+(ctpn_conv3x3_simt) against a float64 torch conv2d evaluated on exactly the operand values the
+bf16 planes carry.  Each case runs in its own process (tests/gpu_checks.py) with a timeout so a
+faulting kernel fails one test instead of the session."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+RELU, POOL, F32 = 1, 2, 4
+
+
+def run_check(*args, timeout=300):
+    cmd = [sys.executable, os.path.join(HERE, "gpu_checks.py")] + [str(a) for a in args]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
+    assert lines, "no result line.\nstdout:\n%s\nstderr:\n%s" % (p.stdout[-2000:], p.stderr[-3000:])
+    res = json.loads(lines[-1])
+    assert res["ok"] and p.returncode == 0, "%s\nstderr:\n%s" % (json.dumps(res), p.stderr[-2000:])
+    return res
+
+
+def conv_args(B, H, W, cin, cout, taps, planes, flags, impl="tc", seed=0):
+    return ["conv", "--B", B, "--H", H, "--W", W, "--cin", cin, "--cout", cout, "--taps", taps, "--planes", planes,
+            "--flags", flags, "--impl", impl, "--seed", seed]
+
+
+# (B, H, W, cin, cout, taps, planes, flags)
+TC_CASES = [
+    (1, 1, 128, 64, 64, 1, 1, F32),            # one tile, one k-block: the minimal tcgen05 round trip
+    (1, 1, 128, 64, 64, 1, 1, 0),              # bf16 plane output
+    (1, 1, 300, 256, 128, 1, 2, F32),          # 1x1 GEMM, ragged M, several k-blocks, 3 plane pairs
+    (1, 8, 16, 64, 64, 9, 1, RELU | F32),      # one 8x16 patch, all 9 taps, zero halo on every side
+    (2, 37, 56, 128, 128, 9, 2, RELU),         # conv5-sized ragged map, batch 2
+    (1, 37, 56, 512, 512, 9, 1, RELU),         # K = 4608, BN = 256, two N tiles
+    (1, 37, 56, 512, 512, 9, 3, RELU),         # six plane pairs (float32-equivalent)
+    (3, 75, 112, 64, 64, 9, 2, RELU | POOL),   # fused 2x2 max-pool, odd height (75 -> 37), > 148 tiles
+    (2, 30, 45, 128, 256, 9, 1, RELU | POOL),  # pool with odd width
+    (1, 150, 225, 64, 128, 9, 2, RELU),        # many tiles per CTA: pipeline phase wrap-around
+    (1, 1, 2072, 512, 1024, 1, 2, F32),        # the BiLSTM x-projection GEMM of one 600x900 image
+    (1, 1, 2072, 512, 64, 1, 2, F32),          # the heads GEMM
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
+def test_conv_tcgen05(case):
+    run_check(*conv_args(*case))
+
+
+SIMT_CASES = [
+    (1, 13, 17, 64, 64, 9, 2, RELU),
+    (2, 20, 30, 64, 128, 9, 3, RELU | POOL),
+    (1, 1, 200, 128, 64, 1, 1, F32),
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES, ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
+def test_conv_simt_reference(case):
+    run_check(*conv_args(*case, impl="simt"))
+
+
+@pytest.mark.parametrize("R,W,planes", [(37, 56, 2), (5, 7, 3), (1184, 56, 1), (600, 100, 2)])
+def test_bilstm_recurrence(R, W, planes):
+    run_check("bilstm", "--R", R, "--W", W, "--planes", planes)

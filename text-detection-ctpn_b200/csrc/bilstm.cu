@@ -1,0 +1,132 @@
+// BiLSTM recurrence over the feature-map width (lib/networks/network.py:93-101: LSTMCell(128)
+// forward and backward over W for every feature-map row, zero initial state).
+//
+// The input projection x.Wx + b for both directions is a plain GEMM (done by ctpn_conv3x3 with
+// taps = 1); this kernel runs the sequential part.  The recurrent matrix Wh is 128 x 512 float32
+// = 256 KiB, more than one SM's shared memory, so a 2-CTA thread-block cluster splits the hidden
+// units: CTA r keeps the 4 x 64 gate columns of units [64r, 64r+64) (128 KiB) resident in shared
+// memory for the whole sequence and the two CTAs exchange their halves of h_t through
+// distributed shared memory once per step.  Each cluster advances RG independent rows of one
+// direction, so Wh is read from shared memory once per RG rows.  All arithmetic is float32.
+//
+// TF 1.3 LSTMCell: gates (i, j, f, o) = [x, h] . kernel + bias;
+//   c = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ctpn {
+
+constexpr int kHid = 128, kGates = 512, kHalf = 64, kLocalCols = 256;
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int RG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, const float *__restrict__ wh_bw,
+              __nv_bfloat16 *__restrict__ out, int R, int W, int planes) {
+  extern __shared__ __align__(16) float smem[];
+  float *Ws = smem;                          // [128][256]  recurrent weights of this CTA's 64 units
+  float *hbuf = Ws + kHid * kLocalCols;      // [2][RG][128] full hidden state, double buffered
+  float *gates = hbuf + 2 * RG * kHid;       // [RG][256]    pre-activations of this CTA's columns
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cid = blockIdx.x >> 1;                       // cluster index
+  const int groups = (R + RG - 1) / RG;
+  const int dir = cid / groups, row0 = (cid % groups) * RG;
+  const int t = threadIdx.x;
+  const int g = t >> 6, ul = t & 63;                     // gate, local unit of this thread's column
+  const int gcol = g * kHid + rank * kHalf + ul;         // column in the 512-wide gate vector
+  const float *wh = dir ? wh_bw : wh_fw;
+  for (int i = t; i < kHid * kLocalCols; i += 256) {
+    const int k = i >> 8, lc = i & 255;
+    Ws[i] = wh[k * kGates + (lc >> 6) * kHid + rank * kHalf + (lc & 63)];
+  }
+  for (int i = t; i < 2 * RG * kHid; i += 256) hbuf[i] = 0.f;
+  float *peer_h = cluster.map_shared_rank(hbuf, rank ^ 1);
+  float c_state[RG / 4];
+#pragma unroll
+  for (int q = 0; q < RG / 4; ++q) c_state[q] = 0.f;
+  cluster.sync();
+
+  const long long plane_stride = (long long)R * W * 2 * kHid;
+  for (int step = 0; step < W; ++step) {
+    const int tpos = dir ? W - 1 - step : step;
+    const float *hc = hbuf + (step & 1) * RG * kHid;
+    float *hn = hbuf + ((step + 1) & 1) * RG * kHid;
+    float *hn_peer = peer_h + ((step + 1) & 1) * RG * kHid;
+    float xp[RG], acc[RG];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const int row = row0 + r;
+      xp[r] = row < R ? __ldg(xproj + ((long long)row * W + tpos) * (2 * kGates) + dir * kGates + gcol) : 0.f;
+      acc[r] = 0.f;
+    }
+#pragma unroll 2
+    for (int k = 0; k < kHid; k += 4) {
+      const float w0 = Ws[(k + 0) * kLocalCols + t], w1 = Ws[(k + 1) * kLocalCols + t];
+      const float w2 = Ws[(k + 2) * kLocalCols + t], w3 = Ws[(k + 3) * kLocalCols + t];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        const float4 h4 = *reinterpret_cast<const float4 *>(hc + r * kHid + k);
+        acc[r] = fmaf(h4.x, w0, acc[r]);
+        acc[r] = fmaf(h4.y, w1, acc[r]);
+        acc[r] = fmaf(h4.z, w2, acc[r]);
+        acc[r] = fmaf(h4.w, w3, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RG; ++r) gates[r * kLocalCols + t] = xp[r] + acc[r];
+    __syncthreads();
+    // cell update: thread -> unit ul, rows (t>>6) + 4q
+#pragma unroll
+    for (int q = 0; q < RG / 4; ++q) {
+      const int r = (t >> 6) + 4 * q;
+      const float gi = gates[r * kLocalCols + ul], gj = gates[r * kLocalCols + 64 + ul];
+      const float gf = gates[r * kLocalCols + 128 + ul], go = gates[r * kLocalCols + 192 + ul];
+      const float c = sigmoidf_acc(gf + 1.0f) * c_state[q] + sigmoidf_acc(gi) * tanhf(gj);
+      const float h = sigmoidf_acc(go) * tanhf(c);
+      c_state[q] = c;
+      const int u = rank * kHalf + ul;
+      hn[r * kHid + u] = h;
+      hn_peer[r * kHid + u] = h;
+      const int row = row0 + r;
+      if (row < R) {
+        __nv_bfloat16 pl[3];
+        split_planes(h, planes, pl);
+        const long long o = ((long long)row * W + tpos) * (2 * kHid) + dir * kHid + u;
+        for (int p = 0; p < planes; ++p) out[p * plane_stride + o] = pl[p];
+      }
+    }
+    cluster.sync();   // h_{t} of both halves visible in both CTAs; also orders the gates[] reuse
+  }
+}
+
+template <int RG>
+static int launch_bilstm(const float *xproj, const float *wh_fw, const float *wh_bw, void *out, int R, int W, int planes,
+                         cudaStream_t st) {
+  const size_t smem = (size_t)(kHid * kLocalCols + 2 * RG * kHid + RG * kLocalCols) * sizeof(float);
+  CTPN_CUDA(cudaFuncSetAttribute(bilstm_kernel<RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int groups = (R + RG - 1) / RG;
+  ProfScope prof("bilstm_recurrent", 2.0 * 2.0 * R * W * 128.0 * 512.0, st);
+  bilstm_kernel<RG><<<2 * 2 * groups, 256, smem, st>>>(xproj, wh_fw, wh_bw, (__nv_bfloat16 *)out, R, W, planes);
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
+}  // namespace ctpn
+
+using namespace ctpn;
+
+extern "C" int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, const float *wh_bw, void *out_planes, int R,
+                                     int W, int planes, void *stream) {
+  CTPN_REQUIRE(xproj && wh_fw && wh_bw && out_planes, "ctpn_bilstm_recurrent: null pointer");
+  CTPN_REQUIRE(R > 0 && W > 0, "ctpn_bilstm_recurrent: bad shape R=%d W=%d", R, W);
+  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_bilstm_recurrent: planes must be 1..3");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R >= 16 * 74) return launch_bilstm<16>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 8 * 74) return launch_bilstm<8>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  return launch_bilstm<4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+}

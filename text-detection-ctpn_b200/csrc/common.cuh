@@ -1,0 +1,73 @@
+// Shared helpers for the ctpn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ctpn_b200.h"
+
+namespace ctpn {
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CTPN_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess) return ::ctpn::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define CTPN_REQUIRE(cond, ...)                \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::ctpn::set_error(__VA_ARGS__);          \
+      return CTPN_ERR_INVALID;                 \
+    }                                          \
+  } while (0)
+
+#define CTPN_LAUNCH_CHECK()                                                    \
+  do {                                                                         \
+    cudaError_t _e = cudaGetLastError();                                       \
+    if (_e != cudaSuccess) return ::ctpn::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+// Optional per-launch timing: when enabled through ctpn_prof_enable(1), every instrumented launch is
+// bracketed by CUDA events on its own stream; `work` is the algorithmic FLOPs (or bytes) of the launch.
+struct ProfScope {
+  ProfScope(const char *label, double work, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st_;
+  int idx_;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- bf16 plane split -------------------------------------------------------------------
+// a = p0 + p1 + p2 with p0 = bf16_rn(a), p1 = bf16_rn(a - p0), p2 = bf16_rn(a - p0 - p1).
+__device__ __forceinline__ void split_planes(float a, int planes, __nv_bfloat16 *p) {
+  __nv_bfloat16 h0 = __float2bfloat16_rn(a);
+  p[0] = h0;
+  if (planes > 1) {
+    float r1 = __fsub_rn(a, __bfloat162float(h0));
+    __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    p[1] = h1;
+    if (planes > 2) {
+      float r2 = __fsub_rn(r1, __bfloat162float(h1));
+      p[2] = __float2bfloat16_rn(r2);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+  return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) {
+  return __uint_as_float(bits16 << 16);
+}
+
+}  // namespace ctpn

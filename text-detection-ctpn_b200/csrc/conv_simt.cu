@@ -1,0 +1,237 @@
+// float32 SIMT kernels around the tensor-core path:
+//   * ctpn_pack_weights   TF-layout float32 weights -> bf16 planes [P][Cout_pad][taps][Cin]
+//   * ctpn_conv1_1        first VGG layer (Cin = 3, K = 27: HBM-bound, no tensor cores); fuses the
+//                         uint8 -> float32 mean subtraction of lib/fast_rcnn/test.py:8-9
+//   * ctpn_conv3x3_simt   same contract as ctpn_conv3x3 with plain float32 FMAs: the in-library
+//                         reference the tests use to validate the tcgen05 kernel
+// Reference semantics: lib/networks/network.py:160-196.
+#include "common.cuh"
+
+namespace ctpn {
+
+// ---- weight packing ---------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float *__restrict__ w, int taps, int cin, int cout, int cout_pad,
+                                    int planes, __nv_bfloat16 *__restrict__ out) {
+  const long long n = (long long)cout_pad * taps * cin;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int ci = (int)(i % cin);
+  const int tap = (int)((i / cin) % taps);
+  const int co = (int)(i / ((long long)cin * taps));
+  float v = co < cout ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
+  __nv_bfloat16 pl[3];
+  split_planes(v, planes, pl);
+  for (int p = 0; p < planes; ++p) out[(long long)p * n + i] = pl[p];
+}
+
+// ---- conv1_1 ----------------------------------------------------------------------------------
+constexpr int kC1TileW = 32, kC1TileH = 8;
+
+template <bool SRC_F32>
+__global__ void __launch_bounds__(kC1TileW *kC1TileH)
+conv1_1_kernel(const void *__restrict__ src, const float *__restrict__ lut, const float *__restrict__ w,
+               const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int B, int H, int W, int planes) {
+  __shared__ float s_in[kC1TileH + 2][kC1TileW + 2][3];
+  __shared__ __align__(16) float s_w[27 * 64];
+  __shared__ float s_b[64];
+  const int tid = threadIdx.y * kC1TileW + threadIdx.x;
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * kC1TileW, y0 = blockIdx.y * kC1TileH;
+  for (int i = tid; i < 27 * 64; i += kC1TileW * kC1TileH) s_w[i] = w[i];
+  if (tid < 64) s_b[tid] = bias[tid];
+  for (int i = tid; i < (kC1TileH + 2) * (kC1TileW + 2) * 3; i += kC1TileW * kC1TileH) {
+    const int c = i % 3, xx = (i / 3) % (kC1TileW + 2), yy = i / (3 * (kC1TileW + 2));
+    const int gx = x0 + xx - 1, gy = y0 + yy - 1;
+    float v = 0.f;   // SAME padding pads the mean-subtracted blob with zeros
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+      const size_t off = (((size_t)b * H + gy) * W + gx) * 3 + c;
+      if (SRC_F32) v = reinterpret_cast<const float *>(src)[off];
+      else v = lut[reinterpret_cast<const uint8_t *>(src)[off] * 3 + c];
+    }
+    s_in[yy][xx][c] = v;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  float in[27];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = s_in[threadIdx.y + ky][threadIdx.x + kx][c];
+  if (x >= W || y >= H) return;
+  const size_t pix = ((size_t)b * H + y) * W + x;
+  const size_t plane_stride = (size_t)B * H * W * 64;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[k * 64 + c0]);
+      const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[k * 64 + c0 + 4]);
+      acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
+      acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
+      acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
+      acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + s_b[c0 + j], 0.f);
+    for (int p = 0; p < planes; ++p) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * j]), h1 = __float2bfloat16_rn(acc[2 * j + 1]);
+        pk[j] = pack_bf16x2(h0, h1);
+        acc[2 * j] = __fsub_rn(acc[2 * j], __bfloat162float(h0));
+        acc[2 * j + 1] = __fsub_rn(acc[2 * j + 1], __bfloat162float(h1));
+      }
+      *reinterpret_cast<uint4 *>(out + p * plane_stride + pix * 64 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// ---- generic float32 SIMT conv on planes --------------------------------------------------------
+// Block: 64 output pixels x 64 output channels, 256 threads (4 x 4 micro-tile each), K in chunks
+// of 32 channels of one tap.  With CTPN_F_POOL the 4 positions of each 2x2 window are evaluated
+// one after the other and max-reduced (4x the loads; this kernel is a reference, not the product).
+constexpr int kSM = 64, kSN = 64, kSK = 32;
+
+__device__ __forceinline__ float load_planes(const __nv_bfloat16 *p, long long off, long long plane_stride, int planes) {
+  float v = __bfloat162float(p[off]);
+  if (planes > 1) v += __bfloat162float(p[off + plane_stride]);
+  if (planes > 2) v += __bfloat162float(p[off + 2 * plane_stride]);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const __nv_bfloat16 *__restrict__ in, const __nv_bfloat16 *__restrict__ wt,
+                 const float *__restrict__ bias, void *__restrict__ out, int B, int H, int W, int Cin, int Cout,
+                 int taps, int planes, int flags) {
+  __shared__ float As[kSK][kSM + 4];
+  __shared__ float Bs[kSK][kSN + 4];
+  const bool pool = flags & CTPN_F_POOL;
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const long long M = (long long)B * Ho * Wo;
+  const long long m0 = (long long)blockIdx.x * kSM;
+  const int n0 = blockIdx.y * kSN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long in_plane = (long long)B * H * W * Cin;
+  const long long w_plane = (long long)Cout * taps * Cin;
+  float best[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) best[i][j] = -INFINITY;
+  const int nsub = pool ? 4 : 1;
+  for (int sub = 0; sub < nsub; ++sub) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int tap = 0; tap < taps; ++tap) {
+      const int dy = taps == 9 ? tap / 3 - 1 : 0, dx = taps == 9 ? tap % 3 - 1 : 0;
+      for (int c0 = 0; c0 < Cin; c0 += kSK) {
+        for (int e = tid; e < kSM * kSK; e += 256) {
+          const int k = e % kSK, pm = e / kSK;
+          const long long mm = m0 + pm;
+          float v = 0.f;
+          if (mm < M) {
+            const int ox = (int)(mm % Wo), oy = (int)((mm / Wo) % Ho), b = (int)(mm / ((long long)Wo * Ho));
+            const int y = (pool ? 2 * oy + (sub >> 1) : oy) + dy, x = (pool ? 2 * ox + (sub & 1) : ox) + dx;
+            if (y >= 0 && y < H && x >= 0 && x < W)
+              v = load_planes(in, (((long long)b * H + y) * W + x) * Cin + c0 + k, in_plane, planes);
+          }
+          As[k][pm] = v;
+        }
+        for (int e = tid; e < kSN * kSK; e += 256) {
+          const int k = e % kSK, pn = e / kSK;
+          Bs[k][pn] = load_planes(wt, ((long long)(n0 + pn) * taps + tap) * Cin + c0 + k, w_plane, planes);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSK; ++k) {
+          const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+          const float4 bb = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+          const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) best[i][j] = fmaxf(best[i][j], acc[i][j]);
+  }
+  const long long out_plane = M * Cout;
+  for (int i = 0; i < 4; ++i) {
+    const long long mm = m0 + ty * 4 + i;
+    if (mm >= M) continue;
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      float v = best[i][j] + bias[co];
+      if (flags & CTPN_F_RELU) v = fmaxf(v, 0.f);
+      if (flags & CTPN_F_OUT_F32) {
+        reinterpret_cast<float *>(out)[mm * Cout + co] = v;
+      } else {
+        __nv_bfloat16 pl[3];
+        split_planes(v, planes, pl);
+        for (int p = 0; p < planes; ++p) reinterpret_cast<__nv_bfloat16 *>(out)[p * out_plane + mm * Cout + co] = pl[p];
+      }
+    }
+  }
+}
+
+}  // namespace ctpn
+
+using namespace ctpn;
+
+extern "C" int ctpn_pack_weights(const float *w_tf, int taps, int cin, int cout, int cout_pad, int planes,
+                                 void *w_planes_out, void *stream) {
+  CTPN_REQUIRE(w_tf && w_planes_out, "ctpn_pack_weights: null pointer");
+  CTPN_REQUIRE(taps > 0 && cin > 0 && cout > 0 && cout_pad >= cout, "ctpn_pack_weights: bad shape");
+  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_pack_weights: planes must be 1..3");
+  const long long n = (long long)cout_pad * taps * cin;
+  pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w_tf, taps, cin, cout, cout_pad, planes, reinterpret_cast<__nv_bfloat16 *>(w_planes_out));
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
+extern "C" int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                            void *out_planes, int B, int H, int W, int planes, void *stream) {
+  CTPN_REQUIRE(src && w_hwio && bias && out_planes, "ctpn_conv1_1: null pointer");
+  CTPN_REQUIRE(src_is_f32 || lut, "ctpn_conv1_1: uint8 input needs the mean-subtraction LUT");
+  CTPN_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "ctpn_conv1_1: bad shape");
+  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_conv1_1: planes must be 1..3");
+  dim3 grid(ceil_div(W, kC1TileW), ceil_div(H, kC1TileH), B), block(kC1TileW, kC1TileH);
+  ProfScope prof("conv1_1", 2.0 * B * H * W * 27.0 * 64.0, (cudaStream_t)stream);
+  if (src_is_f32)
+    conv1_1_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, lut, w_hwio, bias, (__nv_bfloat16 *)out_planes, B, H, W, planes);
+  else
+    conv1_1_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(src, lut, w_hwio, bias, (__nv_bfloat16 *)out_planes, B, H, W, planes);
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
+extern "C" int ctpn_conv3x3_simt(const void *in_planes, const void *w_planes, const float *bias, void *out, int B,
+                                 int H, int W, int cin, int cout, int taps, int planes, int flags, void *stream) {
+  CTPN_REQUIRE(in_planes && w_planes && bias && out, "ctpn_conv3x3_simt: null pointer");
+  CTPN_REQUIRE(taps == 9 || taps == 1, "ctpn_conv3x3_simt: taps must be 9 or 1");
+  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_conv3x3_simt: planes must be 1..3");
+  CTPN_REQUIRE(cin % kSK == 0 && cout % kSN == 0, "ctpn_conv3x3_simt: Cin %% 32 and Cout %% 64 must be 0");
+  const bool pool = flags & CTPN_F_POOL;
+  const long long M = (long long)B * (pool ? H / 2 : H) * (pool ? W / 2 : W);
+  dim3 grid((unsigned)((M + kSM - 1) / kSM), cout / kSN);
+  ProfScope prof("conv_simt", 2.0 * B * H * W * (double)taps * cin * cout, (cudaStream_t)stream);
+  conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)in_planes, (const __nv_bfloat16 *)w_planes,
+                                                           bias, out, B, H, W, cin, cout, taps, planes, flags);
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}

@@ -1,0 +1,208 @@
+"""Engine: host-side driver of the B200 CTPN hot path.
+
+PyTorch is used only as plumbing (device memory, streams, pinned buffers); all
+compute is in libctpn_b200.so (see include/ctpn_b200.h).  One Engine == one GPU.
+
+    eng = Engine(weights, planes=2)              # weights: {tf_variable_name: ndarray}
+    scores, boxes = eng.detect(im)               # == lib.fast_rcnn.test.test_ctpn
+    results = eng.detect_batch(uint8_batch)      # [B,H,W,3] -> list of (scores, boxes)
+
+`planes` selects the arithmetic of the tensor-core layers (see include/ctpn_b200.h):
+1 = bf16 operands, 2 = bf16x2 split (~16 mantissa bits), 3 = bf16x3 split (float32-equivalent
+products); accumulation is always float32.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+# lib/fast_rcnn/config.py:147-183 defaults used by the test path
+DEFAULT_CFG = dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THRESH=0.7, RPN_MIN_SIZE=8,
+                   SCALES=(600,), MAX_SIZE=1000, FEAT_STRIDE=16, ANCHORS_PY2=False)
+
+
+class Engine:
+    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False):
+        if not torch.cuda.is_available():
+            raise N.CtpnError("ctpn_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        N.check(N.lib.ctpn_device_ok(device), "ctpn_device_ok")
+        self.planes = int(planes)
+        self.cfg = dict(DEFAULT_CFG)
+        if cfg:
+            self.cfg.update(cfg)
+        h = C.c_void_p()
+        N.check(N.lib.ctpn_net_create(C.byref(h), self.planes), "ctpn_net_create")
+        self._net = h
+        if conv_simt:
+            N.check(N.lib.ctpn_net_set_option(self._net, b"conv_simt", 1), "set_option")
+        if keep_activations:
+            N.check(N.lib.ctpn_net_set_option(self._net, b"keep_activations", 1), "set_option")
+        self._ws = {}
+        self._pinned = {}
+        if weights is not None:
+            self.load_weights(weights)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_net", None):
+                N.lib.ctpn_net_destroy(self._net)
+                self._net = None
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------
+    def load_weights(self, weights):
+        """weights: dict TF-variable-name -> float32 ndarray, or a path to
+        an .npz with those keys, or a VGG16 .npy dict {layer: {'weights','biases'}} (network.py:40-53)."""
+        if isinstance(weights, str):
+            weights = load_weight_file(weights)
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            N.check(N.lib.ctpn_net_set_weight(self._net, name.encode(), N.ptr(a), a.size), "ctpn_net_set_weight(%s)" % name)
+
+    # ---- buffers ---------------------------------------------------------------------------
+    def _workspace(self, key, nbytes):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    def _pin(self, key, shape, dtype):
+        t = self._pinned.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[key] = t
+        return t
+
+    @staticmethod
+    def feature_hw(H, W):
+        fh, fw = C.c_int(), C.c_int()
+        N.check(N.lib.ctpn_net_feature_hw(H, W, C.byref(fh), C.byref(fw)), "ctpn_net_feature_hw")
+        return fh.value, fw.value
+
+    # ---- stages ----------------------------------------------------------------------------
+    def forward_heads(self, images):
+        """images: CUDA tensor [B,H,W,3], uint8 BGR (mean subtraction fused) or float32 blob
+        (already mean-subtracted, test.py:9).  Returns (rpn_cls_score [B,h,w,20] logits,
+        rpn_bbox_pred [B,h,w,40]) float32 CUDA tensors."""
+        assert images.is_cuda and images.dim() == 4 and images.shape[3] == 3 and images.is_contiguous()
+        is_f32 = images.dtype == torch.float32
+        assert is_f32 or images.dtype == torch.uint8
+        B, H, W, _ = images.shape
+        fh, fw = self.feature_hw(H, W)
+        need = N.lib.ctpn_net_workspace_bytes(self._net, B, H, W)
+        ws = self._workspace("net", need)
+        cls = torch.empty((B, fh, fw, 20), dtype=torch.float32, device=self.device)
+        bbox = torch.empty((B, fh, fw, 40), dtype=torch.float32, device=self.device)
+        N.check(N.lib.ctpn_net_forward(self._net, N.ptr(images), int(is_f32), B, H, W, N.ptr(cls), N.ptr(bbox),
+                                       N.ptr(ws), ws.numel(), N.stream_ptr()), "ctpn_net_forward")
+        return cls, bbox
+
+    def tap(self, name):
+        """Debug: float32 copy of a named activation of the last forward (keep_activations=True)."""
+        cnt = C.c_size_t()
+        N.check(N.lib.ctpn_net_debug_tap(self._net, name.encode(), None, 0, C.byref(cnt), None), "debug_tap")
+        out = torch.empty(cnt.value, dtype=torch.float32, device=self.device)
+        N.check(N.lib.ctpn_net_debug_tap(self._net, name.encode(), N.ptr(out), out.numel(), C.byref(cnt), N.stream_ptr()), "debug_tap")
+        return out
+
+    def proposals(self, cls, bbox, im_info, cls_is_logit=True, cfg=None):
+        """Batched proposal layer (proposal_layer_tf.py:14-157) on CUDA tensors.
+        Returns rois [B,post,5] (score,x1,y1,x2,y2), index [B,post] int32, count [B] int32."""
+        c = dict(self.cfg)
+        if cfg:
+            c.update(cfg)
+        B, H, W, _ = cls.shape
+        pre, post = int(c["RPN_PRE_NMS_TOP_N"]), int(c["RPN_POST_NMS_TOP_N"])
+        NA = H * W * 10
+        max_n = pre if 0 < pre < NA else NA
+        rows = post if post > 0 else max_n
+        need = N.lib.ctpn_proposals_workspace_bytes(B, H, W, pre)
+        ws = self._workspace("prop", need)
+        rois = torch.empty((B, rows, 5), dtype=torch.float32, device=self.device)
+        index = torch.empty((B, rows), dtype=torch.int32, device=self.device)
+        count = torch.empty((B,), dtype=torch.int32, device=self.device)
+        im_info = im_info.to(device=self.device, dtype=torch.float32).contiguous()
+        N.check(N.lib.ctpn_proposals(N.ptr(cls.contiguous()), int(cls_is_logit), N.ptr(bbox.contiguous()), N.ptr(im_info),
+                                     B, H, W, int(c["FEAT_STRIDE"]), pre, post, float(c["RPN_NMS_THRESH"]),
+                                     float(c["RPN_MIN_SIZE"]), int(bool(c["ANCHORS_PY2"])), N.ptr(rois), N.ptr(index),
+                                     N.ptr(count), N.ptr(ws), ws.numel(), N.stream_ptr()), "ctpn_proposals")
+        return rois, index, count
+
+    # ---- public API ------------------------------------------------------------------------
+    def detect_device(self, images, im_info):
+        """images: CUDA [B,H,W,3] uint8/float32; im_info: [B,3] tensor (blob_h, blob_w, scale).
+        Returns device tensors (rois [B,post,5], count [B])."""
+        cls, bbox = self.forward_heads(images)
+        rois, _, count = self.proposals(cls, bbox, im_info, cls_is_logit=True)
+        return rois, count
+
+    def all_gather(self, rois, count):
+        """Multi-GPU (one process per GPU, torch.distributed/NCCL initialised by the caller): every rank
+        contributes the fixed-shape results of its image shard; returns ([world*B,post,5], [world*B])
+        ordered by rank.  The only collective on the path (images are independent)."""
+        import torch.distributed as dist
+        world = dist.get_world_size()
+        all_r = torch.empty((world * rois.shape[0],) + tuple(rois.shape[1:]), dtype=rois.dtype, device=rois.device)
+        all_c = torch.empty((world * count.shape[0],), dtype=count.dtype, device=count.device)
+        dist.all_gather_into_tensor(all_r, rois.contiguous())
+        dist.all_gather_into_tensor(all_c, count.contiguous())
+        return all_r, all_c
+
+    def rois_batch(self, images, im_info=None, gather=False):
+        """images: host ndarray [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
+        im_info: [B,3] (defaults to (H, W, 1.0)).  Returns one float32 [n,5] array per image,
+        rows (score, x1, y1, x2, y2) in blob coordinates -- the 'rois' tensor of the reference
+        graph (network.py:217).  H2D of the inputs and D2H of the results are part of the call.
+        gather=True (multi-GPU): results of all ranks' shards, in rank order."""
+        images = np.ascontiguousarray(images)
+        B, H, W, _ = images.shape
+        dt = torch.uint8 if images.dtype == np.uint8 else torch.float32
+        if dt == torch.float32:
+            images = images.astype(np.float32, copy=False)
+        if im_info is None:
+            im_info = np.array([[H, W, 1.0]] * B, np.float32)
+        stage = self._pin("in", images.shape, dt)
+        stage.numpy()[...] = images
+        info_h = self._pin("info", (B, 3), torch.float32)
+        info_h.numpy()[...] = np.asarray(im_info, np.float32).reshape(B, 3)
+        dev = stage.to(self.device, non_blocking=True)
+        rois, count = self.detect_device(dev, info_h.to(self.device, non_blocking=True))
+        if gather:
+            rois, count = self.all_gather(rois, count)
+        rois_h = self._pin("rois", tuple(rois.shape), torch.float32)
+        cnt_h = self._pin("cnt", tuple(count.shape), torch.int32)
+        rois_h.copy_(rois, non_blocking=True)
+        cnt_h.copy_(count, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [rois_h[b, :int(cnt_h[b])].numpy().copy() for b in range(rois_h.shape[0])]
+
+    def detect_batch(self, images, im_scale=1.0):
+        """Returns a list of (scores [n] f32, boxes [n,4] f32) per image, boxes divided by
+        im_scale exactly as lib/fast_rcnn/test.py:54-57 does."""
+        B, H, W, _ = images.shape
+        info = np.array([[H, W, im_scale]] * B, np.float32)
+        return [(r[:, 0], r[:, 1:5] / np.float32(im_scale)) for r in self.rois_batch(images, info)]
+
+    def detect(self, image, im_scale=1.0):
+        """Single image [H,W,3] -> (scores, boxes); the test_ctpn() contract."""
+        return self.detect_batch(image[None], im_scale)[0]
+
+
+def load_weight_file(path):
+    """.npz with TF variable names, or the reference's VGG .npy dict (network.py:40-53:
+    np.load(..., encoding='latin1').item() -> {layer: {'weights': ..., 'biases': ...}})."""
+    if path.endswith(".npz"):
+        with np.load(path) as z:
+            return {k: z[k] for k in z.files}
+    d = np.load(path, allow_pickle=True, encoding="latin1").item()
+    out = {}
+    for layer, sub in d.items():
+        for k, v in sub.items():
+            out["%s/%s" % (layer, k)] = np.asarray(v, np.float32)
+    return out
