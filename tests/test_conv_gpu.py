@@ -20,6 +20,7 @@ def run_check(*args, timeout=300):
     lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
     assert lines, "no result line.\nstdout:\n%s\nstderr:\n%s" % (p.stdout[-2000:], p.stderr[-3000:])
     res = json.loads(lines[-1])
+    print(" ".join(str(a) for a in args), "->", json.dumps(res))
     assert res["ok"] and p.returncode == 0, "%s\nstderr:\n%s" % (json.dumps(res), p.stderr[-2000:])
     return res
 

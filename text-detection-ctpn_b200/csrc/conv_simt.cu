@@ -25,21 +25,29 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int taps, int c
 }
 
 // ---- conv1_1 ----------------------------------------------------------------------------------
-constexpr int kC1TileW = 32, kC1TileH = 8;
+// 16 threads per pixel, 4 output channels per thread: the 27 x 4 weights of a thread live in
+// registers for the whole CTA, the 27 inputs of a pixel are broadcast shared-memory reads, and a
+// warp's stores cover two pixels x 64 channels = 256 contiguous bytes per plane (fully coalesced;
+// the layer is HBM-write bound: 64 channels x P planes x 2 B per pixel out for 3 B in).
+constexpr int kC1TileW = 32, kC1TileH = 8, kC1Threads = 256;
 
 template <bool SRC_F32>
-__global__ void __launch_bounds__(kC1TileW *kC1TileH)
+__global__ void __launch_bounds__(kC1Threads)
 conv1_1_kernel(const void *__restrict__ src, const float *__restrict__ lut, const float *__restrict__ w,
                const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int B, int H, int W, int planes) {
   __shared__ float s_in[kC1TileH + 2][kC1TileW + 2][3];
-  __shared__ __align__(16) float s_w[27 * 64];
-  __shared__ float s_b[64];
-  const int tid = threadIdx.y * kC1TileW + threadIdx.x;
+  const int tid = threadIdx.x;
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * kC1TileW, y0 = blockIdx.y * kC1TileH;
-  for (int i = tid; i < 27 * 64; i += kC1TileW * kC1TileH) s_w[i] = w[i];
-  if (tid < 64) s_b[tid] = bias[tid];
-  for (int i = tid; i < (kC1TileH + 2) * (kC1TileW + 2) * 3; i += kC1TileW * kC1TileH) {
+  const int cg = tid & 15, slot = tid >> 4;      // channel group (4 channels), pixel slot (16 per pass)
+  float wr[27][4];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(w + k * 64 + cg * 4));
+    wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
+  }
+  const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + cg * 4));
+  for (int i = tid; i < (kC1TileH + 2) * (kC1TileW + 2) * 3; i += kC1Threads) {
     const int c = i % 3, xx = (i / 3) % (kC1TileW + 2), yy = i / (3 * (kC1TileW + 2));
     const int gx = x0 + xx - 1, gy = y0 + yy - 1;
     float v = 0.f;   // SAME padding pads the mean-subtracted blob with zeros
@@ -51,43 +59,40 @@ conv1_1_kernel(const void *__restrict__ src, const float *__restrict__ lut, cons
     s_in[yy][xx][c] = v;
   }
   __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  float in[27];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) in[(ky * 3 + kx) * 3 + c] = s_in[threadIdx.y + ky][threadIdx.x + kx][c];
-  if (x >= W || y >= H) return;
-  const size_t pix = ((size_t)b * H + y) * W + x;
   const size_t plane_stride = (size_t)B * H * W * 64;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 64; c0 += 8) {
-    float acc[8];
+  for (int pass = 0; pass < kC1TileW * kC1TileH / 16; ++pass) {
+    const int pidx = pass * 16 + slot;
+    const int px = pidx % kC1TileW, py = pidx / kC1TileW;
+    const int x = x0 + px, y = y0 + py;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4 *>(&s_w[k * 64 + c0]);
-      const float4 w1 = *reinterpret_cast<const float4 *>(&s_w[k * 64 + c0 + 4]);
-      acc[0] = fmaf(in[k], w0.x, acc[0]); acc[1] = fmaf(in[k], w0.y, acc[1]);
-      acc[2] = fmaf(in[k], w0.z, acc[2]); acc[3] = fmaf(in[k], w0.w, acc[3]);
-      acc[4] = fmaf(in[k], w1.x, acc[4]); acc[5] = fmaf(in[k], w1.y, acc[5]);
-      acc[6] = fmaf(in[k], w1.z, acc[6]); acc[7] = fmaf(in[k], w1.w, acc[7]);
-    }
+      for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j] + s_b[c0 + j], 0.f);
+        for (int c = 0; c < 3; ++c) {
+          const float v = s_in[py + ky][px + kx][c];
+          const int k = (ky * 3 + kx) * 3 + c;
+          acc[0] = fmaf(v, wr[k][0], acc[0]);
+          acc[1] = fmaf(v, wr[k][1], acc[1]);
+          acc[2] = fmaf(v, wr[k][2], acc[2]);
+          acc[3] = fmaf(v, wr[k][3], acc[3]);
+        }
+    if (x >= W || y >= H) continue;
+    acc[0] = fmaxf(acc[0] + bv.x, 0.f); acc[1] = fmaxf(acc[1] + bv.y, 0.f);
+    acc[2] = fmaxf(acc[2] + bv.z, 0.f); acc[3] = fmaxf(acc[3] + bv.w, 0.f);
+    const size_t o = (((size_t)b * H + y) * W + x) * 64 + cg * 4;
     for (int p = 0; p < planes; ++p) {
-      uint32_t pk[4];
+      uint32_t pk[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * j]), h1 = __float2bfloat16_rn(acc[2 * j + 1]);
         pk[j] = pack_bf16x2(h0, h1);
         acc[2 * j] = __fsub_rn(acc[2 * j], __bfloat162float(h0));
         acc[2 * j + 1] = __fsub_rn(acc[2 * j + 1], __bfloat162float(h1));
       }
-      *reinterpret_cast<uint4 *>(out + p * plane_stride + pix * 64 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint2 *>(out + p * plane_stride + o) = make_uint2(pk[0], pk[1]);
     }
   }
 }
@@ -210,7 +215,7 @@ extern "C" int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, c
   CTPN_REQUIRE(src_is_f32 || lut, "ctpn_conv1_1: uint8 input needs the mean-subtraction LUT");
   CTPN_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "ctpn_conv1_1: bad shape");
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_conv1_1: planes must be 1..3");
-  dim3 grid(ceil_div(W, kC1TileW), ceil_div(H, kC1TileH), B), block(kC1TileW, kC1TileH);
+  dim3 grid(ceil_div(W, kC1TileW), ceil_div(H, kC1TileH), B), block(kC1Threads);
   ProfScope prof("conv1_1", 2.0 * B * H * W * 27.0 * 64.0, (cudaStream_t)stream);
   if (src_is_f32)
     conv1_1_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(src, lut, w_hwio, bias, (__nv_bfloat16 *)out_planes, B, H, W, planes);

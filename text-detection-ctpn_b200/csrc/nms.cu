@@ -8,54 +8,48 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "nms_iou.cuh"
 
 namespace ctpn {
 
 typedef unsigned long long u64;
 constexpr int kNmsTile = 64;
 
-__device__ __forceinline__ float box_area(float4 b) {
-  return __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-}
-
-__device__ __forceinline__ float iou_exact(float4 a, float sa, float4 b, float sb) {
-  float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
-  float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
-  float w = fmaxf(0.f, __fadd_rn(__fsub_rn(xx2, xx1), 1.f));
-  float h = fmaxf(0.f, __fadd_rn(__fsub_rn(yy2, yy1), 1.f));
-  float inter = __fmul_rn(w, h);
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
-}
-
-// grid (col_block, row_block, image); 64 threads; thread = one row box against 64 column boxes.
+// grid (G, image); 64 threads.  Each CTA walks (row block, column block) pairs of the upper triangle
+// with stride G; thread = one row box against the 64 boxes of the column block.
 __global__ void __launch_bounds__(kNmsTile)
 nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ counts, int max_n,
-                int col_blocks, float thresh, u64 *__restrict__ mask) {
-  const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z;
-  if (cb < rb) return;
-  int n = counts ? min(counts[img], max_n) : max_n;
-  if (rb * kNmsTile >= n || cb * kNmsTile >= n) return;
+                int col_blocks, float thresh, u64 *__restrict__ mask, const int *__restrict__ gate) {
+  const int img = blockIdx.y;
+  if (gate && gate[img] == 0) return;   // this image is handled by the column-wise path
+  const int n = counts ? min(counts[img], max_n) : max_n;
+  const int nb = (n + kNmsTile - 1) / kNmsTile;
   const float4 *b = boxes + (size_t)img * max_n;
   __shared__ float4 cbox[kNmsTile];
   __shared__ float carea[kNmsTile];
   const int t = threadIdx.x;
-  const int col_size = min(n - cb * kNmsTile, kNmsTile);
-  if (t < col_size) {
-    float4 v = b[cb * kNmsTile + t];
-    cbox[t] = v;
-    carea[t] = box_area(v);
-  }
-  __syncthreads();
-  const int row = rb * kNmsTile + t;
-  if (row < n) {
-    float4 me = b[row];
-    float sme = box_area(me);
-    u64 bits = 0;
-    int start = (rb == cb) ? t + 1 : 0;
-    for (int i = start; i < col_size; ++i) {
-      if (iou_exact(me, sme, cbox[i], carea[i]) > thresh) bits |= 1ULL << i;
+  for (int pair = blockIdx.x; pair < nb * nb; pair += gridDim.x) {
+    const int rb = pair / nb, cb = pair % nb;
+    if (cb < rb) continue;
+    const int col_size = min(n - cb * kNmsTile, kNmsTile);
+    __syncthreads();
+    if (t < col_size) {
+      float4 v = b[cb * kNmsTile + t];
+      cbox[t] = v;
+      carea[t] = box_area(v);
     }
-    mask[((size_t)img * max_n + row) * col_blocks + cb] = bits;
+    __syncthreads();
+    const int row = rb * kNmsTile + t;
+    if (row < n) {
+      float4 me = b[row];
+      float sme = box_area(me);
+      u64 bits = 0;
+      int start = (rb == cb) ? t + 1 : 0;
+      for (int i = start; i < col_size; ++i) {
+        if (iou_exact(me, sme, cbox[i], carea[i]) > thresh) bits |= 1ULL << i;
+      }
+      mask[((size_t)img * max_n + row) * col_blocks + cb] = bits;
+    }
   }
 }
 
@@ -65,8 +59,9 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ counts
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ counts, int max_n,
                 int col_blocks, int max_keep, int keep_stride, int *__restrict__ keep_out,
-                int *__restrict__ num_out) {
+                int *__restrict__ num_out, const int *__restrict__ gate) {
   extern __shared__ u64 remv[];
+  if (gate && gate[blockIdx.x] == 0) return;
   __shared__ u64 diag[kNmsTile];
   __shared__ u64 s_kept;
   __shared__ int s_nkeep;
@@ -132,7 +127,7 @@ static inline int nms_col_blocks(int max_n) { return (max_n + kNmsTile - 1) / kN
 
 int nms_sorted_launch(const float *boxes, const int *counts, int batch, int max_n, float thresh,
                       int max_keep, int keep_stride, int *keep_out, int *num_out, void *workspace,
-                      size_t workspace_bytes, cudaStream_t st) {
+                      size_t workspace_bytes, cudaStream_t st, const int *gate) {
   if (batch <= 0 || max_n <= 0) return CTPN_OK;
   const int cb = nms_col_blocks(max_n);
   size_t need = (size_t)batch * max_n * cb * sizeof(u64);
@@ -142,15 +137,16 @@ int nms_sorted_launch(const float *boxes, const int *counts, int batch, int max_
   }
   CTPN_REQUIRE(((uintptr_t)boxes & 15) == 0, "ctpn_nms_sorted: boxes must be 16-byte aligned");
   u64 *mask = reinterpret_cast<u64 *>(workspace);
-  dim3 grid(cb, cb, batch);
+  long long pairs = (long long)cb * cb;
+  dim3 grid((unsigned)(pairs < 148 * 16 ? pairs : 148 * 16), batch);
   ProfScope prof("nms (mask+scan)", 0.0, st);
-  nms_mask_kernel<<<grid, kNmsTile, 0, st>>>(reinterpret_cast<const float4 *>(boxes), counts, max_n, cb, thresh, mask);
+  nms_mask_kernel<<<grid, kNmsTile, 0, st>>>(reinterpret_cast<const float4 *>(boxes), counts, max_n, cb, thresh, mask, gate);
   CTPN_LAUNCH_CHECK();
   size_t smem = (size_t)cb * sizeof(u64);
   CTPN_REQUIRE(smem <= 200 * 1024, "ctpn_nms_sorted: %d boxes exceed the scan kernel's shared memory", max_n);
   if (smem > 48 * 1024)
     CTPN_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nms_scan_kernel<<<batch, 256, smem, st>>>(mask, counts, max_n, cb, max_keep, keep_stride, keep_out, num_out);
+  nms_scan_kernel<<<batch, 256, smem, st>>>(mask, counts, max_n, cb, max_keep, keep_stride, keep_out, num_out, gate);
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
@@ -190,7 +186,7 @@ extern "C" int ctpn_nms_sorted(const float *boxes, const int *counts, int batch,
   CTPN_REQUIRE(batch >= 0 && max_n >= 0, "ctpn_nms_sorted: negative size");
   int stride = max_keep > 0 ? max_keep : max_n;
   return nms_sorted_launch(boxes, counts, batch, max_n, thresh, max_keep, stride, keep_out, num_out, workspace,
-                           workspace_bytes, (cudaStream_t)stream);
+                           workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int ctpn_nms_host(int *keep_out, int *num_out, const float *boxes_host, int boxes_num, int boxes_dim,
@@ -220,7 +216,7 @@ extern "C" int ctpn_nms_host(int *keep_out, int *num_out, const float *boxes_hos
   int *keep_d = (int *)s.keep;
   int *num_d = keep_d + n;
   rc = nms_sorted_launch((const float *)s.box4, nullptr, 1, boxes_num, nms_overlap_thresh, 0, boxes_num, keep_d, num_d,
-                         s.mask, s.mask_b, st);
+                         s.mask, s.mask_b, st, nullptr);
   if (rc) return rc;
   int num = 0;
   CTPN_CUDA(cudaMemcpyAsync(&num, num_d, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -9,6 +9,7 @@
 // Exactness: all box arithmetic is float32 in the reference's operation order with no FMA
 // contraction; exp() is evaluated in double and rounded once (== oracle exp_mode='rounded').
 #include "common.cuh"
+#include "nms_iou.cuh"
 
 namespace ctpn {
 
@@ -16,7 +17,7 @@ typedef unsigned long long u64;
 
 int nms_sorted_launch(const float *boxes, const int *counts, int batch, int max_n, float thresh,
                       int max_keep, int keep_stride, int *keep_out, int *num_out, void *workspace,
-                      size_t workspace_bytes, cudaStream_t st);
+                      size_t workspace_bytes, cudaStream_t st, const int *gate);
 
 // generate_anchors.py:26 heights -> (y1, y2) of the 10 base anchors; x is always [0, 15].
 __constant__ int c_anchor_y[2][10][2] = {
@@ -33,8 +34,8 @@ __device__ __forceinline__ uint32_t desc_key(float s) {
 __global__ void __launch_bounds__(256)
 proposal_decode_kernel(const float *__restrict__ cls, int cls_is_logit, const float *__restrict__ bbox,
                        const float *__restrict__ im_info, int H, int W, int feat_stride, float min_size,
-                       int py2, float4 *__restrict__ boxes, float *__restrict__ scores,
-                       uint32_t *__restrict__ keys, uint8_t *__restrict__ valid) {
+                       int py2, float nms_thresh, float4 *__restrict__ boxes, float *__restrict__ scores,
+                       uint32_t *__restrict__ keys, uint8_t *__restrict__ valid, int *__restrict__ unstructured) {
   const int NA = H * W * 10;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int img = blockIdx.y;
@@ -84,7 +85,13 @@ proposal_decode_kernel(const float *__restrict__ cls, int cls_is_logit, const fl
   boxes[off] = make_float4(x1, y1, x2, y2);
   scores[off] = score;
   keys[off] = desc_key(score);
-  valid[off] = (ws >= ms && hs >= ms) ? 1 : 0;
+  const bool ok = ws >= ms && hs >= ms;
+  valid[off] = ok ? 1 : 0;
+  // Column structure check for the fast NMS path: a kept box must start exactly at its anchor column,
+  // end within it (<= 1 px shared with the next column) and be wide enough that a 1-px overlap can
+  // never reach the NMS threshold: IoU <= 1 / (w + w' - 1) <= 1 / (2 w_min - 1) < thresh.
+  if (ok && unstructured && (x1 != ax1 || x2 > ax1 + (float)feat_stride || (2.f * ws - 1.f) * nms_thresh <= 1.f))
+    unstructured[img] = 1;
 }
 
 // ---- segmented stable LSD radix sort: one CTA per image, 4 passes of 8 bits ---------------
@@ -206,8 +213,111 @@ __global__ void proposal_emit_kernel(const float4 *__restrict__ sorted_boxes, co
   if (k == 0) count_out[img] = n;
 }
 
+// ---- column-wise NMS ---------------------------------------------------------------------------
+// CTPN proposals of different feature-map columns overlap by at most one pixel column, so greedy NMS
+// over the score-sorted list decomposes EXACTLY into independent per-column problems of <= H*10 boxes
+// (the decode kernel verifies the precondition per image and the generic bitmask
+// path takes over when it does not hold).  One CTA per (column, image): ordered gather of the
+// column's boxes from the sorted list, pairwise mask in shared memory, warp-serial greedy scan.
+constexpr int kColThreads = 256;
+
+__global__ void __launch_bounds__(kColThreads)
+proposal_column_nms_kernel(const float4 *__restrict__ sorted_boxes, const int *__restrict__ sorted_idx,
+                           const int *__restrict__ counts, const int *__restrict__ unstructured, int max_n, int H,
+                           int W, float thresh, uint8_t *__restrict__ kept_flags) {
+  const int col = blockIdx.x, img = blockIdx.y;
+  if (unstructured[img]) return;
+  const int cap = H * 10, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) unsigned char col_smem[];
+  float4 *box = reinterpret_cast<float4 *>(col_smem);
+  u64 *mask = reinterpret_cast<u64 *>(box + cap);
+  const int wc_max = (cap + 63) / 64;
+  float *area = reinterpret_cast<float *>(mask + (size_t)cap * wc_max);
+  int *pos = reinterpret_cast<int *>(area + cap);
+  __shared__ int warp_cnt[kColThreads / 32];
+  const int n = counts[img];
+  const float4 *sb = sorted_boxes + (size_t)img * max_n;
+  const int *si = sorted_idx + (size_t)img * max_n;
+  int total = 0;
+  for (int base = 0; base < n; base += kColThreads) {
+    const int r = base + tid;
+    const bool pred = r < n && ((si[r] / 10) % W == col);
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, tile = 0;
+#pragma unroll
+    for (int w = 0; w < kColThreads / 32; ++w) { const int c = warp_cnt[w]; tile += c; if (w < warp) before += c; }
+    if (pred) {
+      const int k = total + before + __popc(bal & ((1u << lane) - 1u));
+      if (k < cap) { pos[k] = r; const float4 b = sb[r]; box[k] = b; area[k] = box_area(b); }
+    }
+    total += tile;
+    __syncthreads();
+  }
+  const int nc = min(total, cap);
+  const int wc = (nc + 63) / 64;
+  for (int item = tid; item < nc * wc; item += kColThreads) {
+    const int i = item / wc, wj = item % wc;
+    const float4 me = box[i];
+    const float sme = area[i];
+    u64 bits = 0;
+    const int j0 = wj * 64;
+    for (int jj = max(0, i + 1 - j0); jj < 64 && j0 + jj < nc; ++jj)
+      if (iou_exact(me, sme, box[j0 + jj], area[j0 + jj]) > thresh) bits |= 1ULL << jj;
+    mask[(size_t)i * wc + wj] = bits;
+  }
+  __syncthreads();
+  if (warp == 0) {   // lane l owns word l of the running suppression vector (wc <= 32)
+    u64 remv = 0;
+    uint8_t *kf = kept_flags + (size_t)img * max_n;
+    for (int i = 0; i < nc; ++i) {
+      const u64 word = __shfl_sync(0xffffffffu, remv, i >> 6);
+      const bool keep = !((word >> (i & 63)) & 1ULL);
+      if (keep && lane < wc) remv |= mask[(size_t)i * wc + lane];
+      if (lane == 0) kf[pos[i]] = keep ? 1 : 0;
+    }
+  }
+}
+
+// first `post` kept positions of every image, in sorted (score) order
+__global__ void __launch_bounds__(1024)
+proposal_compact_kernel(const uint8_t *__restrict__ kept_flags, const int *__restrict__ counts,
+                        const int *__restrict__ unstructured, int max_n, int post, int *__restrict__ keep,
+                        int *__restrict__ num) {
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (unstructured[img]) return;
+  __shared__ int warp_cnt[32];
+  const int n = counts[img];
+  const uint8_t *kf = kept_flags + (size_t)img * max_n;
+  int total = 0;
+  for (int base = 0; base < n && total < post; base += 1024) {
+    const int r = base + tid;
+    const bool pred = r < n && kf[r] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, tile = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { const int c = warp_cnt[w]; tile += c; if (w < warp) before += c; }
+    if (pred) {
+      const int k = total + before + __popc(bal & ((1u << lane) - 1u));
+      if (k < post) keep[(size_t)img * post + k] = r;
+    }
+    total += tile;
+    __syncthreads();
+  }
+  if (tid == 0) num[img] = min(total, post);
+}
+
+static size_t column_smem_bytes(int H) {
+  const size_t cap = (size_t)H * 10, wc = (cap + 63) / 64;
+  return cap * sizeof(float4) + cap * wc * sizeof(u64) + cap * sizeof(float) + cap * sizeof(int);
+}
+
 struct ProposalWs {
   size_t boxes, scores, keys, valid, buf_a, buf_b, sorted_boxes, sorted_idx, counts, keep, num, mask, total;
+  size_t unstructured, kept_flags;
   size_t mask_bytes;
 };
 
@@ -226,6 +336,8 @@ static ProposalWs proposal_layout(int batch, int NA, int max_n, int post) {
   w.counts = take((size_t)batch * sizeof(int));
   w.keep = take((size_t)batch * post * sizeof(int));
   w.num = take((size_t)batch * sizeof(int));
+  w.unstructured = take((size_t)batch * sizeof(int));
+  w.kept_flags = take((size_t)batch * max_n);
   w.mask_bytes = ctpn_nms_workspace_bytes(batch, max_n);
   w.mask = take(w.mask_bytes);
   w.total = o;
@@ -275,15 +387,33 @@ extern "C" int ctpn_proposals(const float *cls, int cls_is_logit, const float *b
   int *num = (int *)(ws + w.num);
   dim3 g1(ceil_div(NA, 256), batch);
   ProfScope prof_all("proposals (decode+sort+nms+emit)", (double)batch * NA * 24.0, st);
+  // column-wise NMS is possible when one column's boxes fit in shared memory and columns do not overlap
+  const size_t col_smem = column_smem_bytes(H);
+  const bool try_columns = feat_stride >= 16 && col_smem <= 200 * 1024 && H * 10 <= 2048 && W <= 65535 &&
+                           !getenv("CTPN_GENERIC_NMS");
+  int *unstructured = (int *)(ws + w.unstructured);
+  CTPN_CUDA(cudaMemsetAsync(unstructured, 0, (size_t)batch * sizeof(int), st));
   proposal_decode_kernel<<<g1, 256, 0, st>>>(cls, cls_is_logit, bbox, im_info, H, W, feat_stride, min_size,
-                                             anchors_py2 ? 1 : 0, boxes, scores, keys, valid);
+                                             anchors_py2 ? 1 : 0, nms_thresh, boxes, scores, keys, valid,
+                                             try_columns ? unstructured : nullptr);
   CTPN_LAUNCH_CHECK();
   CTPN_CUDA(cudaFuncSetAttribute(proposal_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
   proposal_sort_kernel<<<batch, kSortThreads, kSortSmem, st>>>(keys, valid, boxes, NA, max_n, (uint2 *)(ws + w.buf_a),
                                                        (uint2 *)(ws + w.buf_b), sorted_boxes, sorted_idx, counts);
   CTPN_LAUNCH_CHECK();
+  if (try_columns) {
+    uint8_t *kept_flags = (uint8_t *)(ws + w.kept_flags);
+    if (col_smem > 48 * 1024)
+      CTPN_CUDA(cudaFuncSetAttribute(proposal_column_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
+    proposal_column_nms_kernel<<<dim3(W, batch), kColThreads, col_smem, st>>>(sorted_boxes, sorted_idx, counts, unstructured,
+                                                                           max_n, H, W, nms_thresh, kept_flags);
+    CTPN_LAUNCH_CHECK();
+    proposal_compact_kernel<<<batch, 1024, 0, st>>>(kept_flags, counts, unstructured, max_n, post, keep, num);
+    CTPN_LAUNCH_CHECK();
+  }
+  // generic bitmask NMS: every image when the column path is off, else only images flagged unstructured
   int rc = nms_sorted_launch((const float *)sorted_boxes, counts, batch, max_n, nms_thresh, post, post, keep, num,
-                             ws + w.mask, w.mask_bytes, st);
+                             ws + w.mask, w.mask_bytes, st, try_columns ? unstructured : nullptr);
   if (rc) return rc;
   dim3 g3(ceil_div(out_rows, 128), batch);
   proposal_emit_kernel<<<g3, 128, 0, st>>>(sorted_boxes, sorted_idx, scores, keep, num, NA, max_n, out_rows, post, rois_out,

@@ -155,20 +155,30 @@ class Engine:
         return all_r, all_c
 
     def rois_batch(self, images, im_info=None, gather=False):
-        """images: host ndarray [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
+        """images: host ndarray or (pinned) CPU tensor [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
         im_info: [B,3] (defaults to (H, W, 1.0)).  Returns one float32 [n,5] array per image,
         rows (score, x1, y1, x2, y2) in blob coordinates -- the 'rois' tensor of the reference
         graph (network.py:217).  H2D of the inputs and D2H of the results are part of the call.
         gather=True (multi-GPU): results of all ranks' shards, in rank order."""
-        images = np.ascontiguousarray(images)
-        B, H, W, _ = images.shape
-        dt = torch.uint8 if images.dtype == np.uint8 else torch.float32
-        if dt == torch.float32:
-            images = images.astype(np.float32, copy=False)
+        if isinstance(images, torch.Tensor):
+            # a pinned host tensor is transferred as is (no staging copy)
+            assert images.device.type == "cpu" and images.dtype in (torch.uint8, torch.float32)
+            B, H, W, _ = images.shape
+            stage = images.contiguous()
+            if not stage.is_pinned():
+                pinned = self._pin("in", tuple(stage.shape), stage.dtype)
+                pinned.copy_(stage)
+                stage = pinned
+        else:
+            images = np.ascontiguousarray(images)
+            B, H, W, _ = images.shape
+            dt = torch.uint8 if images.dtype == np.uint8 else torch.float32
+            if dt == torch.float32:
+                images = images.astype(np.float32, copy=False)
+            stage = self._pin("in", images.shape, dt)
+            stage.numpy()[...] = images
         if im_info is None:
             im_info = np.array([[H, W, 1.0]] * B, np.float32)
-        stage = self._pin("in", images.shape, dt)
-        stage.numpy()[...] = images
         info_h = self._pin("info", (B, 3), torch.float32)
         info_h.numpy()[...] = np.asarray(im_info, np.float32).reshape(B, 3)
         dev = stage.to(self.device, non_blocking=True)
