@@ -141,6 +141,13 @@ int ctpn_net_feature_hw(int H, int W, int *fh, int *fw);
 int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_f32, size_t capacity,
                        size_t *count, void *stream);
 
+/* ---- diagnostics (not on the product path) ----------------------------------------------
+ * Hardware probe used by tests/probe_umma_view.py: reads a [rows][64] bf16 matrix through a UMMA
+ * K-major SWIZZLE_128B descriptor that starts at row `row0` with `group_stride_rows` between 8-row
+ * groups, against the identity, and returns the 128x64 values the tensor core fetched. */
+int ctpn_probe_umma_view(const void *a_bf16, const void *identity_bf16, int rows, int row0,
+                         int group_stride_rows, int base_offset_mode, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,46 +1,65 @@
 // 3x3 SAME convolution / 1x1 matmul on bf16 "planes" with 5th-generation tensor cores.
 //
-// Implicit GEMM: M = output pixels (a TH x TW patch of one image per CTA tile, TH*TW = 128),
-// N = output channels (BN per tile), K = taps * Cin in blocks of 64 channels.
-//   * A operand: for each tap the TH x TW x 64 input patch shifted by (dy, dx) is fetched with
-//     ONE 4-D TMA box load from the NHWC tensor; out-of-image elements are zero-filled by the
-//     TMA unit, which implements SAME padding and ragged image edges without any halo buffer.
-//     The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, i.e. exactly
-//     the canonical K-major UMMA layout.
-//   * B operand: weights [P][Cout][taps][Cin] viewed as a 2-D K-major matrix, 2-D TMA box.
-//   * D: float32 accumulators in TMEM (double buffered: the epilogue of tile i overlaps the
-//     MMAs of tile i+1), tcgen05.mma issued by one thread, completion via tcgen05.commit.
-//   * float32-faithful mode: activations/weights are split into P bf16 planes; all plane pairs
-//     (i, j) with i + j < P are accumulated into the same TMEM tile (1, 3 or 6 MMAs per k-step).
-//   * epilogue (4 warps = 128 TMEM lanes): tcgen05.ld -> +bias -> ReLU -> optional fused 2x2
-//     max-pool (warp shuffles: the 2x2 window of a pixel lives in lanes l, l^1, l^TW, l^TW^1)
-//     -> re-split into planes -> 16-byte global stores (or float32 output).
-// Persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer and
-// TMEM owner, warps 2-5 epilogue.  Reference semantics: lib/networks/network.py:160-196.
+// Implicit GEMM: M = 128 output pixels (a 16 x 8 patch of one image per CTA tile), N = BN output
+// channels, K = taps * Cin in blocks of 64 channels.
+//   * A operand: per channel block ONE 4-D TMA box load brings the (16+2) x (8+2) x 64 halo patch of the
+//     NHWC input into shared memory (128-byte swizzle; out-of-image elements are zero-filled by the TMA
+//     unit = SAME padding and ragged edges for free).  The nine filter taps are then served as nine
+//     shifted VIEWS of that one patch: the UMMA shared-memory descriptor starts at halo row
+//     (ky * 10 + kx) and steps 10 rows between its 8-row groups (tile row th <-> halo row th + ky).  The
+//     tensor core applies the 128B swizzle to the absolute shared-memory address, so un-aligned views of
+//     a TMA-written buffer are consistent (verified by tests/probe_umma_view.py on B200).  This cuts the
+//     L2 -> SM traffic of A by 6.4x compared with one TMA load per tap.
+//   * B operand: weights [P][Cout][taps][Cin] viewed as a 2-D K-major matrix, one 2-D TMA box per
+//     (tap, channel block), in its own ring of stages.
+//   * D: float32 accumulators in TMEM; tcgen05.mma issued by one thread, completion via tcgen05.commit.
+//     With P > 1 planes the plane-0 x plane-0 products go to a "main" accumulator and all cross-plane
+//     products to a second one (the tensor core truncates when adding into float32).
+//   * epilogue (4 warps = 128 TMEM lanes): tcgen05.ld -> (+cross) -> +bias -> ReLU -> optional fused 2x2
+//     max-pool (warp shuffles: the window of a pixel lives in lanes l, l^1, l^8, l^9) -> re-split into
+//     planes -> 16-byte global stores (or float32 output).
+// Persistent CTAs (one per SM), warp-specialised: warp 0 weight (B) producer, warp 1 MMA issuer + TMEM
+// owner, warps 2-5 epilogue, warp 6 activation (A) producer.  Reference: lib/networks/network.py:160-196.
 #include <cuda.h>
 
-#include <mutex>
+#include <algorithm>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace ctpn {
 
 struct ConvTcParams {
   int B, H, W, Cin, Cout, taps, planes, flags;
   int tiles_x, tiles_y, tiles_n, total_tiles;
-  int TH, TW, tw_log2;
+  int TH, TW, tw_log2;      // tile geometry (pixels); TH * TW == 128
+  int PW;                   // halo patch width in pixels (= shared-memory rows per patch row)
+  int patch_bytes;          // bytes of one plane's patch slot (1024-aligned)
+  int patch_tx_bytes;       // bytes the TMA box actually transfers per plane
+  int group_stride_bytes;   // UMMA stride between 8-row groups of the A view
   int cout_pad;
   int Ho, Wo;
-  int stages;
+  int stages_a, stages_b;
+  int nbuf;                 // TMEM tile buffers: 2 = epilogue overlaps the next tile's MMAs, 1 = serialised
   const float *bias;
   void *out;
   long long out_plane_stride;   // elements between output planes
 };
 
-constexpr int kTcThreads = 192;
-constexpr int kABytes = 128 * 128;   // 128 pixels x 64 bf16
+constexpr int kTcThreads = 224;
 constexpr int kMaxStages = 8;
+constexpr int kCtrlBytes = 8 * (4 * kMaxStages + 4) + 16;
+
+__device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_t group_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(group_stride_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -51,22 +70,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t kIdesc = umma_idesc_bf16(128, BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t stage0 = (raw + 1023u) & ~1023u;
+  const uint32_t ring_a = (raw + 1023u) & ~1023u;
   const int P = p.planes;
-  const uint32_t stage_bytes = (uint32_t)P * (kABytes + kBBytes);
-  uint8_t *ctrl = smem_raw + (stage0 - raw) + (size_t)p.stages * stage_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ctrl);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
-  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ctrl + 8 * (2 * kMaxStages + 4));
+  const uint32_t a_stage = (uint32_t)P * p.patch_bytes, b_stage = (uint32_t)P * kBBytes;
+  const uint32_t ring_b = ring_a + (uint32_t)p.stages_a * a_stage;
+  uint8_t *ctrl = smem_raw + (ring_b - raw) + (size_t)p.stages_b * b_stage;
+  const uint32_t fullA = smem_u32(ctrl), emptyA = fullA + 8 * kMaxStages;
+  const uint32_t fullB = emptyA + 8 * kMaxStages, emptyB = fullB + 8 * kMaxStages;
+  const uint32_t tfull0 = emptyB + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ctrl + 8 * (4 * kMaxStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(fullA + 8 * s, 1);
+      mbar_init(emptyA + 8 * s, 1);
+      mbar_init(fullB + 8 * s, 1);
+      mbar_init(emptyB + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -74,14 +96,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     fence_mbar_init();
   }
-  // TMEM: two tile buffers (epilogue of tile i overlaps the MMAs of tile i+1).  With P > 1 every
-  // buffer holds TWO accumulators: "main" receives the plane-0 x plane-0 products, "cross" all the
-  // 2^-8 .. 2^-16 smaller cross-plane products.  The tensor core truncates (does not round) when it
-  // adds into the float32 accumulator; keeping the small terms out of the big accumulator keeps
-  // their truncation error proportional to THEIR magnitude (measured: 3-6x lower end-to-end error).
-  const uint32_t acc_cols = (P > 1 ? 2u : 1u) * BN;
+  const uint32_t acc_cols = (P > 1 ? 2u : 1u) * BN;   // main (+ cross) accumulator columns per tile buffer
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.nbuf * acc_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -91,28 +108,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int kblocks = p.Cin / 64;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int halo = p.taps == 9 ? 1 : 0;
 
-  if (warp == 0) {
+  if (warp == 6) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== activation (A) producer: one halo patch per plane per channel block =====
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+        const int mt = tile / p.tiles_n;
         const int b = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int y0 = (r / p.tiles_x) * p.TH, x0 = (r % p.tiles_x) * p.TW;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(full0 + 8 * s, stage_bytes);
-            const uint32_t sa = stage0 + (uint32_t)s * stage_bytes;
-            const uint32_t sb = sa + (uint32_t)P * kABytes;
+        const int y0 = (r / p.tiles_x) * p.TH - halo, x0 = (r % p.tiles_x) * p.TW - halo;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(emptyA + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(fullA + 8 * s, (uint32_t)P * (uint32_t)p.patch_tx_bytes);
+          for (int pl = 0; pl < P; ++pl)
+            tma_load_4d(&tmap_a, fullA + 8 * s, ring_a + s * a_stage + pl * p.patch_bytes, kb * 64, x0, y0, pl * p.B + b);
+          if (++s == p.stages_a) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0) {
+      // ===== weight (B) producer: one [BN][64] tile per plane per (channel block, tap) =====
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(emptyB + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(fullB + 8 * s, b_stage);
             for (int pl = 0; pl < P; ++pl)
-              tma_load_4d(&tmap_a, full0 + 8 * s, sa + pl * kABytes, kb * 64, x0 + dx, y0 + dy, pl * p.B + b);
-            for (int pl = 0; pl < P; ++pl)
-              tma_load_2d(&tmap_b, full0 + 8 * s, sb + pl * kBBytes, tap * p.Cin + kb * 64, pl * p.cout_pad + nt * BN);
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+              tma_load_2d(&tmap_b, fullB + 8 * s, ring_b + s * b_stage + pl * kBBytes, tap * p.Cin + kb * 64,
+                          pl * p.cout_pad + nt * BN);
+            if (++s == p.stages_b) { s = 0; ph ^= 1u; }
           }
         }
       }
@@ -120,39 +150,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      int s = 0, a = 0;
-      uint32_t ph = 0, aph = 0;
+      int sa = 0, sb = 0, a = 0;
+      uint32_t pha = 0, phb = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)a * acc_cols, d_cross = d_main + BN;
         uint32_t accum_main = 0, accum_cross = 0;
-        const int ksteps = p.taps * kblocks;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(full0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = stage0 + (uint32_t)s * stage_bytes;
-          const uint32_t sb = sa + (uint32_t)P * kABytes;
-          for (int i = 0; i < P; ++i) {
-            for (int j = 0; j < P - i; ++j) {
-              const uint64_t da = umma_desc_k_sw128(sa + i * kABytes);
-              const uint64_t db = umma_desc_k_sw128(sb + j * kBBytes);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(fullA + 8 * sa, pha);
+          const uint32_t pa = ring_a + sa * a_stage;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(fullB + 8 * sb, phb);
+            tc_fence_after();
+            const uint32_t pb = ring_b + sb * b_stage;
+            const uint32_t view = p.taps == 9 ? (uint32_t)((tap / 3) * p.PW + tap % 3) * 128u : 0u;
+            for (int i = 0; i < P; ++i) {
+              for (int j = 0; j < P - i; ++j) {
+                const uint64_t da = umma_desc_a_view(pa + i * p.patch_bytes + view, (uint32_t)p.group_stride_bytes);
+                const uint64_t db = umma_desc_k_sw128(pb + j * kBBytes);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {   // 64 / UMMA_K(16); +32 B == +2 in the >>4 address field
-                if (i + j == 0) { mma_bf16_ss(d_main, da + 2ull * k, db + 2ull * k, kIdesc, accum_main); accum_main = 1; }
-                else { mma_bf16_ss(d_cross, da + 2ull * k, db + 2ull * k, kIdesc, accum_cross); accum_cross = 1; }
+                for (int k = 0; k < 4; ++k) {   // 64 / UMMA_K(16); +32 B == +2 in the >>4 address field
+                  if (i + j == 0) { mma_bf16_ss(d_main, da + 2ull * k, db + 2ull * k, kIdesc, accum_main); accum_main = 1; }
+                  else { mma_bf16_ss(d_cross, da + 2ull * k, db + 2ull * k, kIdesc, accum_cross); accum_cross = 1; }
+                }
               }
             }
+            mma_commit(emptyB + 8 * sb);   // weight stage free once these MMAs have read it
+            if (++sb == p.stages_b) { sb = 0; phb ^= 1u; }
           }
-          mma_commit(empty0 + 8 * s);   // frees the smem stage when these MMAs have read it
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          mma_commit(emptyA + 8 * sa);     // halo patch free after its last tap
+          if (++sa == p.stages_a) { sa = 0; pha ^= 1u; }
         }
-        mma_commit(tfull0 + 8 * a);      // accumulator complete -> epilogue
-        a ^= 1;
-        if (a == 0) aph ^= 1u;
+        mma_commit(tfull0 + 8 * a);        // accumulator complete -> epilogue
+        if (++a == p.nbuf) { a = 0; aph ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue warps (TMEM lane quarter = warp id % 4) =====
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;
@@ -240,78 +274,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * a);
-      a ^= 1;
-      if (a == 0) aph ^= 1u;
+      if (++a == p.nbuf) { a = 0; aph ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * acc_cols);
+    tmem_dealloc(tmem_base, (uint32_t)p.nbuf * acc_cols);
   }
 }
 
 // ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int get_encode(EncodeTiledFn *out) {
-  static EncodeTiledFn fn = nullptr;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!fn) {
-    void *sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CTPN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
-    if (!sym || qres != cudaDriverEntryPointSuccess) {
-      set_error("cuTensorMapEncodeTiled is not available from this driver");
-      return CTPN_ERR_CUDA;
-    }
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  *out = fn;
-  return CTPN_OK;
-}
-
-static int encode(EncodeTiledFn fn, CUtensorMap *m, void *addr, int rank, const cuuint64_t *dims,
-                  const cuuint64_t *strides, const cuuint32_t *box) {
-  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, addr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
-    return CTPN_ERR_CUDA;
-  }
-  return CTPN_OK;
-}
-
-// Pick the TH x TW (=128) pixel patch with the fewest wasted lanes.  Pooling needs both rows and
-// both columns of every 2x2 window inside one warp: TW in {4, 8, 16}, TH and TW even.
-static void pick_patch(int H, int W, bool pool, int *TH, int *TW) {
-  const int cands[6][2] = {{8, 16}, {16, 8}, {4, 32}, {2, 64}, {1, 128}, {32, 4}};
-  long long best = -1;
-  for (auto &c : cands) {
-    if (pool && !(c[1] == 16 || c[1] == 8 || c[1] == 4)) continue;
-    long long tiles = (long long)ceil_div(H, c[0]) * ceil_div(W, c[1]);
-    if (best < 0 || tiles < best) { best = tiles; *TH = c[0]; *TW = c[1]; }
-  }
-}
-
 static int g_num_sms = 0;
+
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 template <int BN>
 static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
-  const size_t stage_bytes = (size_t)p.planes * (kABytes + BN * 128);
-  const size_t ctrl = 8 * (2 * kMaxStages + 4) + 16;
-  const size_t budget = 227 * 1024;
-  int stages = (int)((budget - 1024 - ctrl) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (const char *e = getenv("CTPN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
-  CTPN_REQUIRE(stages >= 1, "conv_tc: a pipeline stage (%zu B) does not fit in shared memory", stage_bytes);
-  p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + ctrl;
+  const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
+  const size_t budget = 227 * 1024 - 1024 - kCtrlBytes;
+  // activation ring: two stages when they leave room for at least two weight stages, else one
+  int sa = (2 * a_stage + 2 * b_stage <= budget) ? 2 : 1;
+  if (p.taps == 1) sa = (int)std::min<size_t>(4, std::max<size_t>(1, (budget / 2) / a_stage));
+  CTPN_REQUIRE(sa * a_stage + b_stage <= budget, "conv_tc: pipeline stages (%zu + %zu B) do not fit in shared memory", a_stage, b_stage);
+  int sb = (int)((budget - sa * a_stage) / b_stage);
+  if (sb > kMaxStages) sb = kMaxStages;
+  sa = std::max(1, std::min(sa, env_int("CTPN_TC_STAGES_A", sa)));
+  sb = std::max(1, std::min(sb, env_int("CTPN_TC_STAGES_B", sb)));
+  p.stages_a = sa;
+  p.stages_b = sb;
+  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kCtrlBytes;
   CTPN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   char label[128];
@@ -342,15 +338,25 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
     CTPN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   EncodeTiledFn enc = nullptr;
-  int rc = get_encode(&enc);
+  int rc = tma_get_encode(&enc);
   if (rc) return rc;
 
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = B; p.H = H; p.W = W; p.Cin = cin; p.Cout = cout; p.taps = taps; p.planes = planes; p.flags = flags;
-  pick_patch(H, W, pool, &p.TH, &p.TW);
-  p.tw_log2 = 0;
-  while ((1 << p.tw_log2) < p.TW) ++p.tw_log2;
+  if (taps == 9) {   // 16 x 8 pixel tile: one 8-row UMMA group per tile row, halo patch 18 x 10
+    p.TH = 16; p.TW = 8; p.tw_log2 = 3;
+    p.PW = 10;
+    p.group_stride_bytes = p.PW * 128;
+    p.patch_tx_bytes = p.PW * 18 * 128;
+    p.patch_bytes = (int)align_up((size_t)p.patch_tx_bytes, 1024);
+  } else {           // flat 128-pixel tile along W (callers pass matmuls as H = 1)
+    p.TH = 1; p.TW = 128; p.tw_log2 = 7;
+    p.PW = 128;
+    p.group_stride_bytes = 1024;
+    p.patch_tx_bytes = 128 * 128;
+    p.patch_bytes = 128 * 128;
+  }
   p.tiles_x = ceil_div(W, p.TW);
   p.tiles_y = ceil_div(H, p.TH);
   p.Ho = pool ? H / 2 : H;
@@ -360,27 +366,28 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.out_plane_stride = (long long)B * p.Ho * p.Wo * cout;
   p.cout_pad = cout;
 
-  int BN = planes == 1 ? 256 : 128;
-  if (const char *e = getenv("CTPN_TC_BN")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) BN = v; }
-  if (planes > 1 && BN > 128) BN = 128;   // two accumulators per tile buffer: 4 * BN TMEM columns <= 512
+  int BN = env_int("CTPN_TC_BN", planes == 3 ? 128 : 256);
+  if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
   while (BN > cout || cout % BN) BN >>= 1;
   p.tiles_n = cout / BN;
+  p.nbuf = ((planes > 1 ? 2 : 1) * BN * 2 <= 512) ? 2 : 1;   // 512 TMEM columns per SM
   const long long total = (long long)B * p.tiles_x * p.tiles_y * p.tiles_n;
   CTPN_REQUIRE(total < (1ll << 31), "ctpn_conv3x3: too many tiles");
   p.total_tiles = (int)total;
 
   CUtensorMap ta, tb;
   {
+    const int halo = taps == 9 ? 1 : 0;
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes * B};
     cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    if ((rc = encode(enc, &ta, const_cast<void *>(in_planes), 4, dims, strides, box))) return rc;
+    cuuint32_t box[4] = {64, (cuuint32_t)p.PW, (cuuint32_t)(p.TH + 2 * halo), 1};
+    if ((rc = tma_encode_bf16(enc, &ta, const_cast<void *>(in_planes), 4, dims, strides, box))) return rc;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)planes * cout};
     cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
-    if ((rc = encode(enc, &tb, const_cast<void *>(w_planes), 2, dims, strides, box))) return rc;
+    if ((rc = tma_encode_bf16(enc, &tb, const_cast<void *>(w_planes), 2, dims, strides, box))) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
