@@ -246,6 +246,7 @@ def main():
                                  "each algorithmic MAC costs %d bf16 MMAs" % (a.planes, mma_per_mac)},
             "stage_ms_per_step": dict({"conv_tc 3x3 (13 launches)": conv_ms, "conv_tc 1x1 GEMMs (3 launches)": sum(p["ms"] for p in gemm) / K}, **other_ms),
             "proposals_per_image": n_props,
+            "layers": [{"kernel": q["kernel"], "ms": q["ms"] / K, "alg_tflops": q["work"] / max(q["ms"], 1e-9) / 1e9} for q in conv + gemm],
         }
         if world == 1 and a.cpu_sample > 0:
             rate, cores, dt = cpu_oracle_rate(a.cpu_sample, H, W)

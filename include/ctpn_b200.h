@@ -148,6 +148,11 @@ int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_f32, size_t
 int ctpn_probe_umma_view(const void *a_bf16, const void *identity_bf16, int rows, int row0,
                          int group_stride_rows, int base_offset_mode, float *out, void *stream);
 
+/* Hardware probe: every CTA issues n_mma 128 x bn x 16 bf16 MMAs with a tcgen05.commit every
+ * `commit_every` MMAs and (lag > 0) waits on each commit `lag` commits later.  Timed by the caller. */
+int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
+                        int grid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,7 @@ struct ConvTcParams {
   int cout_pad;
   int Ho, Wo;
   int stages_a, stages_b;
+  int debug;                // CTPN_TC_DEBUG bits (perf experiments only): 1 skip B loads, 2 skip A loads, 4 skip MMAs, 8 skip stores
   int nbuf;                 // TMEM tile buffers: 2 = epilogue overlaps the next tile's MMAs, 1 = serialised
   const float *bias;
   void *out;
@@ -80,7 +81,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tfull0 = emptyB + 8 * kMaxStages, tempty0 = tfull0 + 16;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ctrl + 8 * (4 * kMaxStages + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle so the compiler knows it is warp-uniform: the role loops below are executed by
+  // whole warps with uniform control flow and only the instruction issue is predicated on one elected lane --
+  // otherwise every TMA / tcgen05 instruction gets wrapped in a per-lane 'waterfall' loop (3x slower issue).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
@@ -111,7 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int halo = p.taps == 9 ? 1 : 0;
 
   if (warp == 6) {
-    if (lane == 0) {
+    {
       // ===== activation (A) producer: one halo patch per plane per channel block =====
       int s = 0;
       uint32_t ph = 0;
@@ -121,15 +125,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int y0 = (r / p.tiles_x) * p.TH - halo, x0 = (r % p.tiles_x) * p.TW - halo;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(emptyA + 8 * s, ph ^ 1u);
-          mbar_arrive_expect_tx(fullA + 8 * s, (uint32_t)P * (uint32_t)p.patch_tx_bytes);
-          for (int pl = 0; pl < P; ++pl)
-            tma_load_4d(&tmap_a, fullA + 8 * s, ring_a + s * a_stage + pl * p.patch_bytes, kb * 64, x0, y0, pl * p.B + b);
+          if (elect_one()) {
+            if (p.debug & 2) { mbar_arrive(fullA + 8 * s); }
+            else {
+              mbar_arrive_expect_tx(fullA + 8 * s, (uint32_t)P * (uint32_t)p.patch_tx_bytes);
+              for (int pl = 0; pl < P; ++pl)
+                tma_load_4d(&tmap_a, fullA + 8 * s, ring_a + s * a_stage + pl * p.patch_bytes, kb * 64, x0, y0, pl * p.B + b);
+            }
+          }
+          __syncwarp();
           if (++s == p.stages_a) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===== weight (B) producer: one [BN][64] tile per plane per (channel block, tap) =====
       int s = 0;
       uint32_t ph = 0;
@@ -138,18 +148,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           for (int tap = 0; tap < p.taps; ++tap) {
             mbar_wait(emptyB + 8 * s, ph ^ 1u);
-            mbar_arrive_expect_tx(fullB + 8 * s, b_stage);
-            for (int pl = 0; pl < P; ++pl)
-              tma_load_2d(&tmap_b, fullB + 8 * s, ring_b + s * b_stage + pl * kBBytes, tap * p.Cin + kb * 64,
-                          pl * p.cout_pad + nt * BN);
+            if (elect_one()) {
+              if (p.debug & 1) { mbar_arrive(fullB + 8 * s); }
+              else {
+                mbar_arrive_expect_tx(fullB + 8 * s, b_stage);
+                for (int pl = 0; pl < P; ++pl)
+                  tma_load_2d(&tmap_b, fullB + 8 * s, ring_b + s * b_stage + pl * kBBytes, tap * p.Cin + kb * 64,
+                              pl * p.cout_pad + nt * BN);
+              }
+            }
+            __syncwarp();
             if (++s == p.stages_b) { s = 0; ph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
       int sa = 0, sb = 0, a = 0;
       uint32_t pha = 0, phb = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -165,7 +181,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t pb = ring_b + sb * b_stage;
             const uint32_t view = p.taps == 9 ? (uint32_t)((tap / 3) * p.PW + tap % 3) * 128u : 0u;
-            for (int i = 0; i < P; ++i) {
+            if (elect_one()) {
+            for (int i = 0; i < P && !(p.debug & 4); ++i) {
               for (int j = 0; j < P - i; ++j) {
                 const uint64_t da = umma_desc_a_view(pa + i * p.patch_bytes + view, (uint32_t)p.group_stride_bytes);
                 const uint64_t db = umma_desc_k_sw128(pb + j * kBBytes);
@@ -177,12 +194,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
             mma_commit(emptyB + 8 * sb);   // weight stage free once these MMAs have read it
+            }
+            __syncwarp();
+            accum_main = 1;
+            accum_cross = 1;
             if (++sb == p.stages_b) { sb = 0; phb ^= 1u; }
           }
-          mma_commit(emptyA + 8 * sa);     // halo patch free after its last tap
+          if (elect_one()) mma_commit(emptyA + 8 * sa);     // halo patch free after its last tap
+          __syncwarp();
           if (++sa == p.stages_a) { sa = 0; pha ^= 1u; }
         }
-        mma_commit(tfull0 + 8 * a);        // accumulator complete -> epilogue
+        if (elect_one()) mma_commit(tfull0 + 8 * a);        // accumulator complete -> epilogue
+        __syncwarp();
         if (++a == p.nbuf) { a = 0; aph ^= 1u; }
       }
     }
@@ -248,7 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], p.TW));
           }
         }
-        if (ok && c0 < p.Cout) {
+        if (ok && c0 < p.Cout && !(p.debug & 8)) {
           if (out_f32) {
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.Cout + c0);
 #pragma unroll
@@ -365,6 +388,7 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.out = out;
   p.out_plane_stride = (long long)B * p.Ho * p.Wo * cout;
   p.cout_pad = cout;
+  p.debug = env_int("CTPN_TC_DEBUG", 0);
 
   int BN = env_int("CTPN_TC_BN", planes == 3 ? 128 : 256);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;

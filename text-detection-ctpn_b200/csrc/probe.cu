@@ -93,3 +93,80 @@ extern "C" int ctpn_probe_umma_view(const void *a, const void *ident, int rows, 
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
+
+// ---- probe 2: sustained tcgen05.mma issue rate vs commit / barrier-wait cadence ------------------
+// Every CTA (one per SM) issues `n_mma` 128 x BN x 16 bf16 MMAs on a fixed (zeroed) shared-memory tile,
+// with a tcgen05.commit every `commit_every` MMAs and, optionally, a wait on that commit's mbarrier
+// `lag` commits later (lag 0 = never wait until the end).  Answers: does a commit stall the tensor pipe?
+namespace ctpn {
+
+template <int BN>
+__global__ void __launch_bounds__(128, 1)
+probe_mma_rate_kernel(int n_mma, int commit_every, int lag, int alternate_acc, int fence_each) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sa = (raw + 1023u) & ~1023u, sb = sa + 16384;
+  __shared__ uint64_t bars[64];
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (16384 + BN * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem_raw + (sa - raw))[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 64; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0) {   // whole warp, uniform control flow
+    const uint32_t idesc = umma_idesc_bf16(128, BN);
+    const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+    int commits = 0, waited = 0;
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t d = tmem + ((alternate_acc && (i & 4)) ? BN : 0);
+      if (elect_one()) mma_bf16_ss(d, da + 2ull * (i & 3), db + 2ull * (i & 3), idesc, i > 7);
+      __syncwarp();
+      if ((i + 1) % commit_every == 0) {
+        if (elect_one()) mma_commit(smem_u32(&bars[commits & 31]));
+        __syncwarp();
+        ++commits;
+        if (lag > 0 && commits - waited > lag) {
+          mbar_wait(smem_u32(&bars[waited & 31]), (waited >> 5) & 1);
+          if (fence_each) tc_fence_after();
+          ++waited;
+        }
+      }
+    }
+    if (lag > 0)
+      while (waited < commits) { mbar_wait(smem_u32(&bars[waited & 31]), (waited >> 5) & 1); ++waited; }
+    if (elect_one()) mma_commit(smem_u32(&bars[40]));      // final: everything issued so far has completed
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[40]), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace ctpn
+
+extern "C" int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
+                                   int grid, void *stream) {
+  CTPN_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ctpn_probe_mma_rate: bn must be 64/128/256");
+  CTPN_REQUIRE(n_mma > 0 && commit_every > 0 && lag >= 0 && lag < 32 && grid > 0, "ctpn_probe_mma_rate: bad arguments");
+  const size_t smem = 1024 + 16384 + (size_t)bn * 128;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CTPN_LAUNCH_PROBE(BN)                                                                                      \
+  do {                                                                                                             \
+    CTPN_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    probe_mma_rate_kernel<BN><<<grid, 128, smem, st>>>(n_mma, commit_every, lag, alternate_acc, fence_each);       \
+  } while (0)
+  if (bn == 256) CTPN_LAUNCH_PROBE(256);
+  else if (bn == 128) CTPN_LAUNCH_PROBE(128);
+  else CTPN_LAUNCH_PROBE(64);
+#undef CTPN_LAUNCH_PROBE
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}

@@ -146,13 +146,8 @@ class Engine:
         """Multi-GPU (one process per GPU, torch.distributed/NCCL initialised by the caller): every rank
         contributes the fixed-shape results of its image shard; returns ([world*B,post,5], [world*B])
         ordered by rank.  The only collective on the path (images are independent)."""
-        import torch.distributed as dist
-        world = dist.get_world_size()
-        all_r = torch.empty((world * rois.shape[0],) + tuple(rois.shape[1:]), dtype=rois.dtype, device=rois.device)
-        all_c = torch.empty((world * count.shape[0],), dtype=count.dtype, device=count.device)
-        dist.all_gather_into_tensor(all_r, rois.contiguous())
-        dist.all_gather_into_tensor(all_c, count.contiguous())
-        return all_r, all_c
+        from .dist import gather_results
+        return gather_results(rois, count)
 
     def rois_batch(self, images, im_info=None, gather=False):
         """images: host ndarray or (pinned) CPU tensor [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);

@@ -19,6 +19,8 @@ class Graph:
 
     def sub_graphs_connected(self):
         g = self.graph
+        if g.shape[0] == 0:
+            return []
         has_in = g.any(axis=0)
         has_out = g.any(axis=1)
         first_out = g.argmax(axis=1)          # index of the first out-edge (other.py:27)
