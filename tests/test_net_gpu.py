@@ -144,6 +144,10 @@ def test_batch_equals_singles_and_simt_cross_check(weights):
         s, b = eng.detect(ims[i])
         np.testing.assert_array_equal(s, batch[i][0])
         np.testing.assert_array_equal(b, batch[i][1])
+    streamed = list(eng.rois_batches([ims, ims[::-1].copy()]))          # pipelined API == per-batch API
+    for i in range(3):
+        np.testing.assert_array_equal(streamed[0][i][:, 0], batch[i][0])
+        np.testing.assert_array_equal(streamed[1][2 - i][:, 0], batch[i][0])
     ref = Engine(weights, planes=2, conv_simt=True)          # float32 SIMT convolutions, same planes
     c1, b1 = eng.forward_heads(torch.from_numpy(ims).cuda())
     c2, b2 = ref.forward_heads(torch.from_numpy(ims).cuda())

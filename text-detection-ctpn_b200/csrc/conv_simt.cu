@@ -25,30 +25,30 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int taps, int c
 }
 
 // ---- conv1_1 ----------------------------------------------------------------------------------
-// 16 threads per pixel, 4 output channels per thread: the 27 x 4 weights of a thread live in
-// registers for the whole CTA, the 27 inputs of a pixel are broadcast shared-memory reads, and a
-// warp's stores cover two pixels x 64 channels = 256 contiguous bytes per plane (fully coalesced;
-// the layer is HBM-write bound: 64 channels x P planes x 2 B per pixel out for 3 B in).
-constexpr int kC1TileW = 32, kC1TileH = 8, kC1Threads = 256;
+// Lane = one pair of output channels (its 27 x 2 weights live in registers), warp = one tile row, and each
+// pass computes 4 horizontally adjacent pixels from 3 x 18 input floats fetched with broadcast LDS.128:
+// 216 FMAs per 15 shared-memory loads.  A warp's store covers one pixel x 64 channels = 128 contiguous
+// bytes per plane.  The layer is HBM-write bound: 64 channels x P planes x 2 B per pixel out for 3 B in.
+constexpr int kC1TileW = 32, kC1TileH = 8, kC1Threads = 256, kC1Row = 104;   // row pitch: 34 * 3 floats padded to 16 B
 
 template <bool SRC_F32>
-__global__ void __launch_bounds__(kC1Threads)
+__global__ void __launch_bounds__(kC1Threads, 2)
 conv1_1_kernel(const void *__restrict__ src, const float *__restrict__ lut, const float *__restrict__ w,
                const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out, int B, int H, int W, int planes) {
-  __shared__ float s_in[kC1TileH + 2][kC1TileW + 2][3];
-  const int tid = threadIdx.x;
+  __shared__ __align__(16) float s_in[kC1TileH + 2][kC1Row];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * kC1TileW, y0 = blockIdx.y * kC1TileH;
-  const int cg = tid & 15, slot = tid >> 4;      // channel group (4 channels), pixel slot (16 per pass)
-  float wr[27][4];
+  float wr[27][2];
 #pragma unroll
   for (int k = 0; k < 27; ++k) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(w + k * 64 + cg * 4));
-    wr[k][0] = v.x; wr[k][1] = v.y; wr[k][2] = v.z; wr[k][3] = v.w;
+    const float2 v = __ldg(reinterpret_cast<const float2 *>(w + k * 64 + lane * 2));
+    wr[k][0] = v.x; wr[k][1] = v.y;
   }
-  const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + cg * 4));
+  const float2 bv = __ldg(reinterpret_cast<const float2 *>(bias + lane * 2));
   for (int i = tid; i < (kC1TileH + 2) * (kC1TileW + 2) * 3; i += kC1Threads) {
-    const int c = i % 3, xx = (i / 3) % (kC1TileW + 2), yy = i / (3 * (kC1TileW + 2));
+    const int xc = i % ((kC1TileW + 2) * 3), yy = i / ((kC1TileW + 2) * 3);
+    const int c = xc % 3, xx = xc / 3;
     const int gx = x0 + xx - 1, gy = y0 + yy - 1;
     float v = 0.f;   // SAME padding pads the mean-subtracted blob with zeros
     if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
@@ -56,43 +56,50 @@ conv1_1_kernel(const void *__restrict__ src, const float *__restrict__ lut, cons
       if (SRC_F32) v = reinterpret_cast<const float *>(src)[off];
       else v = lut[reinterpret_cast<const uint8_t *>(src)[off] * 3 + c];
     }
-    s_in[yy][xx][c] = v;
+    s_in[yy][xc] = v;
   }
   __syncthreads();
   const size_t plane_stride = (size_t)B * H * W * 64;
+  const int y = y0 + warp;
+  if (y >= H) return;
 #pragma unroll 1
-  for (int pass = 0; pass < kC1TileW * kC1TileH / 16; ++pass) {
-    const int pidx = pass * 16 + slot;
-    const int px = pidx % kC1TileW, py = pidx / kC1TileW;
-    const int x = x0 + px, y = y0 + py;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int g = 0; g < kC1TileW / 4; ++g) {
+    float in[3][20];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int ky = 0; ky < 3; ++ky) {
+      const float4 *row = reinterpret_cast<const float4 *>(&s_in[warp + ky][12 * g]);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float v = s_in[py + ky][px + kx][c];
-          const int k = (ky * 3 + kx) * 3 + c;
-          acc[0] = fmaf(v, wr[k][0], acc[0]);
-          acc[1] = fmaf(v, wr[k][1], acc[1]);
-          acc[2] = fmaf(v, wr[k][2], acc[2]);
-          acc[3] = fmaf(v, wr[k][3], acc[3]);
-        }
-    if (x >= W || y >= H) continue;
-    acc[0] = fmaxf(acc[0] + bv.x, 0.f); acc[1] = fmaxf(acc[1] + bv.y, 0.f);
-    acc[2] = fmaxf(acc[2] + bv.z, 0.f); acc[3] = fmaxf(acc[3] + bv.w, 0.f);
-    const size_t o = (((size_t)b * H + y) * W + x) * 64 + cg * 4;
-    for (int p = 0; p < planes; ++p) {
-      uint32_t pk[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(acc[2 * j]), h1 = __float2bfloat16_rn(acc[2 * j + 1]);
-        pk[j] = pack_bf16x2(h0, h1);
-        acc[2 * j] = __fsub_rn(acc[2 * j], __bfloat162float(h0));
-        acc[2 * j + 1] = __fsub_rn(acc[2 * j + 1], __bfloat162float(h1));
+      for (int q = 0; q < 5; ++q) {       // 18 floats needed; the 5th vector over-reads 2 floats of padding / next pixels
+        const float4 v = row[q];
+        in[ky][4 * q] = v.x; in[ky][4 * q + 1] = v.y; in[ky][4 * q + 2] = v.z; in[ky][4 * q + 3] = v.w;
       }
-      *reinterpret_cast<uint2 *>(out + p * plane_stride + o) = make_uint2(pk[0], pk[1]);
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = in[ky][(px + kx) * 3 + c];
+            const int k = (ky * 3 + kx) * 3 + c;
+            a0 = fmaf(v, wr[k][0], a0);
+            a1 = fmaf(v, wr[k][1], a1);
+          }
+      const int x = x0 + 4 * g + px;
+      if (x < W) {
+        a0 = fmaxf(a0 + bv.x, 0.f);
+        a1 = fmaxf(a1 + bv.y, 0.f);
+        const size_t o = (((size_t)b * H + y) * W + x) * 64 + lane * 2;
+        for (int p = 0; p < planes; ++p) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+          *reinterpret_cast<uint32_t *>(out + p * plane_stride + o) = pack_bf16x2(h0, h1);
+          a0 = __fsub_rn(a0, __bfloat162float(h0));
+          a1 = __fsub_rn(a1, __bfloat162float(h1));
+        }
+      }
     }
   }
 }

@@ -390,7 +390,9 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.cout_pad = cout;
   p.debug = env_int("CTPN_TC_DEBUG", 0);
 
-  int BN = env_int("CTPN_TC_BN", planes == 3 ? 128 : 256);
+  // N tile: 256 halves the A traffic per MAC but, with two accumulators per tile (P > 1), leaves no TMEM for
+  // double buffering -- worth it only when the K loop is long enough to amortise the serialised epilogue.
+  int BN = env_int("CTPN_TC_BN", (planes == 1 || (planes == 2 && taps * cin >= 9 * 256)) ? 256 : 128);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
   while (BN > cout || cout % BN) BN >>= 1;
   p.tiles_n = cout / BN;

@@ -187,6 +187,59 @@ class Engine:
         torch.cuda.current_stream().synchronize()
         return [rois_h[b, :int(cnt_h[b])].numpy().copy() for b in range(rois_h.shape[0])]
 
+    def rois_batches(self, batches, im_info=None):
+        """Pipelined version of rois_batch for a stream of equally shaped host batches (pinned uint8/float32
+        CPU tensors or ndarrays): the H2D copy of batch k+1 runs on a side stream while batch k is computed,
+        and results are read back with one small D2H per batch.  Yields the rois_batch() result of every batch
+        in order."""
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+
+        def stage(images):
+            if isinstance(images, torch.Tensor):
+                src = images.contiguous()
+                if not src.is_pinned():
+                    pinned = self._pin("in", tuple(src.shape), src.dtype)
+                    pinned.copy_(src)
+                    src = pinned
+            else:
+                arr = np.ascontiguousarray(images)
+                dt = torch.uint8 if arr.dtype == np.uint8 else torch.float32
+                src = self._pin("in", arr.shape, dt)
+                src.numpy()[...] = arr if dt == torch.uint8 else arr.astype(np.float32, copy=False)
+            with torch.cuda.stream(copy_stream):
+                dev = src.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return dev, ev
+
+        it = iter(batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            dev, ev = nxt
+            try:
+                nxt = stage(next(it))          # overlaps with the compute enqueued below
+            except StopIteration:
+                nxt = None
+            B, H, W, _ = dev.shape
+            info = im_info if im_info is not None else np.array([[H, W, 1.0]] * B, np.float32)
+            info_h = self._pin("info", (B, 3), torch.float32)
+            info_h.numpy()[...] = np.asarray(info, np.float32).reshape(B, 3)
+            main.wait_event(ev)
+            rois, count = self.detect_device(dev, info_h.to(self.device, non_blocking=True))
+            dev.record_stream(main)
+            rois_h = self._pin("rois", tuple(rois.shape), torch.float32)
+            cnt_h = self._pin("cnt", tuple(count.shape), torch.int32)
+            rois_h.copy_(rois, non_blocking=True)
+            cnt_h.copy_(count, non_blocking=True)
+            main.synchronize()
+            yield [rois_h[b, :int(cnt_h[b])].numpy().copy() for b in range(rois_h.shape[0])]
+
     def detect_batch(self, images, im_scale=1.0):
         """Returns a list of (scores [n] f32, boxes [n,4] f32) per image, boxes divided by
         im_scale exactly as lib/fast_rcnn/test.py:54-57 does."""
