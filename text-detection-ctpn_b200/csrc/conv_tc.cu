@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_
   return d;
 }
 
-template <int BN>
+template <int BN, int P, int TAPS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvTcParams p) {
@@ -72,7 +72,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring_a = (raw + 1023u) & ~1023u;
-  const int P = p.planes;
   const uint32_t a_stage = (uint32_t)P * p.patch_bytes, b_stage = (uint32_t)P * kBBytes;
   const uint32_t ring_b = ring_a + (uint32_t)p.stages_a * a_stage;
   uint8_t *ctrl = smem_raw + (ring_b - raw) + (size_t)p.stages_b * b_stage;
@@ -112,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int kblocks = p.Cin / 64;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int halo = p.taps == 9 ? 1 : 0;
+  constexpr int halo = TAPS == 9 ? 1 : 0;
 
   if (warp == 6) {
     {
@@ -146,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
-          for (int tap = 0; tap < p.taps; ++tap) {
+          for (int tap = 0; tap < TAPS; ++tap) {
             mbar_wait(emptyB + 8 * s, ph ^ 1u);
             if (elect_one()) {
               if (p.debug & 1) { mbar_arrive(fullB + 8 * s); }
@@ -166,38 +165,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     {
       // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
+      // Descriptors are (per-stage low word) + compile-time offsets: planes, taps and k-slices are fully
+      // unrolled so every tcgen05.mma needs only two uniform adds (N = 64 tiles are issue-rate bound).
+      constexpr uint32_t kPatch16 = (TAPS == 9 ? 23552u : 16384u) >> 4;   // plane stride of the A stage, in 16-B units
+      constexpr uint32_t kB16 = (uint32_t)kBBytes >> 4;
+      constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);    // SBO | version | SWIZZLE_128B
+      const uint32_t hi_a = ((uint32_t)p.group_stride_bytes >> 4) | (1u << 14) | (2u << 29);
       int sa = 0, sb = 0, a = 0;
       uint32_t pha = 0, phb = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);
         tc_fence_after();
         const uint32_t d_main = tmem_base + (uint32_t)a * acc_cols, d_cross = d_main + BN;
-        uint32_t accum_main = 0, accum_cross = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(fullA + 8 * sa, pha);
-          const uint32_t pa = ring_a + sa * a_stage;
-          for (int tap = 0; tap < p.taps; ++tap) {
+          const uint32_t a_lo = (((ring_a + sa * a_stage) >> 4) & 0x3FFFu) | (1u << 16);
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
             mbar_wait(fullB + 8 * sb, phb);
             tc_fence_after();
-            const uint32_t pb = ring_b + sb * b_stage;
-            const uint32_t view = p.taps == 9 ? (uint32_t)((tap / 3) * p.PW + tap % 3) * 128u : 0u;
-            if (elect_one()) {
-            for (int i = 0; i < P && !(p.debug & 4); ++i) {
-              for (int j = 0; j < P - i; ++j) {
-                const uint64_t da = umma_desc_a_view(pa + i * p.patch_bytes + view, (uint32_t)p.group_stride_bytes);
-                const uint64_t db = umma_desc_k_sw128(pb + j * kBBytes);
+            const uint32_t b_lo = (((ring_b + sb * b_stage) >> 4) & 0x3FFFu) | (1u << 16);
+            constexpr int kPW = 10;
+            const uint32_t view16 = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + tap % 3) * 8u : 0u;
+            const uint32_t not_first = (kb | tap) != 0;
+            if (elect_one() && !(p.debug & 4)) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {   // 64 / UMMA_K(16); +32 B == +2 in the >>4 address field
-                  if (i + j == 0) { mma_bf16_ss(d_main, da + 2ull * k, db + 2ull * k, kIdesc, accum_main); accum_main = 1; }
-                  else { mma_bf16_ss(d_cross, da + 2ull * k, db + 2ull * k, kIdesc, accum_cross); accum_cross = 1; }
+              for (int i = 0; i < P; ++i) {
+#pragma unroll
+                for (int j = 0; j < P - i; ++j) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {   // 64 / UMMA_K(16); +32 B == +2 in the >>4 address field
+                    const uint64_t da = ((uint64_t)hi_a << 32) | (a_lo + i * kPatch16 + view16 + 2u * k);
+                    const uint64_t db = ((uint64_t)kHiB << 32) | (b_lo + j * kB16 + 2u * k);
+                    if (i + j == 0) mma_bf16_ss(d_main, da, db, kIdesc, k == 0 ? not_first : 1u);
+                    else mma_bf16_ss(d_cross, da, db, kIdesc, (k == 0 && i == 0 && j == 1) ? not_first : 1u);
+                  }
                 }
               }
             }
-            mma_commit(emptyB + 8 * sb);   // weight stage free once these MMAs have read it
-            }
             __syncwarp();
-            accum_main = 1;
-            accum_cross = 1;
+            if (elect_one()) mma_commit(emptyB + 8 * sb);   // weight stage free once these MMAs have read it
+            __syncwarp();
             if (++sb == p.stages_b) { sb = 0; phb ^= 1u; }
           }
           if (elect_one()) mma_commit(emptyA + 8 * sa);     // halo patch free after its last tap
@@ -316,7 +324,7 @@ static int env_int(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int BN>
+template <int BN, int P, int TAPS>
 static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
   const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
   const size_t budget = 227 * 1024 - 1024 - kCtrlBytes;
@@ -331,12 +339,12 @@ static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams 
   p.stages_a = sa;
   p.stages_b = sb;
   const size_t smem = 1024 + sa * a_stage + sb * b_stage + kCtrlBytes;
-  CTPN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CTPN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, P, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   char label[128];
   snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d p%d bn%d", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, p.planes, BN);
   ProfScope prof(label, 2.0 * p.B * p.H * p.W * (double)p.taps * p.Cin * p.Cout, st);
-  conv_tc_kernel<BN><<<grid, kTcThreads, smem, st>>>(ta, tb, p);
+  conv_tc_kernel<BN, P, TAPS><<<grid, kTcThreads, smem, st>>>(ta, tb, p);
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
@@ -394,6 +402,7 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   // double buffering -- worth it only when the K loop is long enough to amortise the serialised epilogue.
   int BN = env_int("CTPN_TC_BN", (planes == 1 || (planes == 2 && taps * cin >= 9 * 256)) ? 256 : 128);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
+  if (planes == 3 && BN > 128) BN = 128;   // three planes of a 256-wide weight tile do not fit the stage budget
   while (BN > cout || cout % BN) BN >>= 1;
   p.tiles_n = cout / BN;
   p.nbuf = ((planes > 1 ? 2 : 1) * BN * 2 <= 512) ? 2 : 1;   // 512 TMEM columns per SM
@@ -416,9 +425,15 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
     if ((rc = tma_encode_bf16(enc, &tb, const_cast<void *>(w_planes), 2, dims, strides, box))) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  switch (BN) {
-    case 256: return launch_bn<256>(ta, tb, p, st);
-    case 128: return launch_bn<128>(ta, tb, p, st);
-    default: return launch_bn<64>(ta, tb, p, st);
-  }
+#define CTPN_TC_CASE(BN_, P_, T_) \
+  if (BN == BN_ && planes == P_ && taps == T_) return launch_bn<BN_, P_, T_>(ta, tb, p, st)
+  CTPN_TC_CASE(256, 1, 9); CTPN_TC_CASE(128, 1, 9); CTPN_TC_CASE(64, 1, 9);
+  CTPN_TC_CASE(256, 2, 9); CTPN_TC_CASE(128, 2, 9); CTPN_TC_CASE(64, 2, 9);
+  CTPN_TC_CASE(128, 3, 9); CTPN_TC_CASE(64, 3, 9);
+  CTPN_TC_CASE(256, 1, 1); CTPN_TC_CASE(128, 1, 1); CTPN_TC_CASE(64, 1, 1);
+  CTPN_TC_CASE(256, 2, 1); CTPN_TC_CASE(128, 2, 1); CTPN_TC_CASE(64, 2, 1);
+  CTPN_TC_CASE(128, 3, 1); CTPN_TC_CASE(64, 3, 1);
+#undef CTPN_TC_CASE
+  set_error("ctpn_conv3x3: no kernel for BN=%d planes=%d taps=%d", BN, planes, taps);
+  return CTPN_ERR_INVALID;
 }

@@ -197,6 +197,10 @@ class Engine:
             copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
 
+        bufs = {}          # two persistent device input buffers, used alternately
+        done = [None, None]  # event: compute that read buffer i has been enqueued and finished
+        counter = [0]
+
         def stage(images):
             if isinstance(images, torch.Tensor):
                 src = images.contiguous()
@@ -209,11 +213,19 @@ class Engine:
                 dt = torch.uint8 if arr.dtype == np.uint8 else torch.float32
                 src = self._pin("in", arr.shape, dt)
                 src.numpy()[...] = arr if dt == torch.uint8 else arr.astype(np.float32, copy=False)
+            slot = counter[0] & 1
+            counter[0] += 1
+            key = (slot, tuple(src.shape), src.dtype)
+            if key not in bufs:
+                bufs[key] = torch.empty(tuple(src.shape), dtype=src.dtype, device=self.device)
+            dev = bufs[key]
             with torch.cuda.stream(copy_stream):
-                dev = src.to(self.device, non_blocking=True)
+                if done[slot] is not None:
+                    copy_stream.wait_event(done[slot])     # the previous user of this buffer has finished
+                dev.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return dev, ev
+            return dev, ev, slot
 
         it = iter(batches)
         try:
@@ -221,7 +233,7 @@ class Engine:
         except StopIteration:
             return
         while nxt is not None:
-            dev, ev = nxt
+            dev, ev, slot = nxt
             try:
                 nxt = stage(next(it))          # overlaps with the compute enqueued below
             except StopIteration:
@@ -232,7 +244,8 @@ class Engine:
             info_h.numpy()[...] = np.asarray(info, np.float32).reshape(B, 3)
             main.wait_event(ev)
             rois, count = self.detect_device(dev, info_h.to(self.device, non_blocking=True))
-            dev.record_stream(main)
+            done[slot] = torch.cuda.Event()
+            done[slot].record(main)
             rois_h = self._pin("rois", tuple(rois.shape), torch.float32)
             cnt_h = self._pin("cnt", tuple(count.shape), torch.int32)
             rois_h.copy_(rois, non_blocking=True)
