@@ -199,6 +199,9 @@ def main():
     value = world * B * K / (ms / 1e3)
     # ---- e2e: host buffers through the public API ----
     eng.rois_batch(host, gather=world > 1)
+    if world == 1:
+        for _ in eng.rois_batches(host for _ in range(2)):   # warm the streaming path (side stream, double buffers)
+            pass
     barrier()
     t0 = time.perf_counter()
     if world > 1:

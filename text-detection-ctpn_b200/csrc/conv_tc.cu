@@ -51,6 +51,8 @@ struct ConvTcParams {
 constexpr int kTcThreads = 224;
 constexpr int kMaxStages = 8;
 constexpr int kCtrlBytes = 8 * (4 * kMaxStages + 4) + 16;
+constexpr int kStagePitch = 80;                    // bytes per pixel row of the epilogue staging buffer (64 B + 16 B pad)
+constexpr int kStageBytes = 4 * 32 * kStagePitch;  // one 32-pixel x 32-channel bf16 block per epilogue warp
 
 __device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_t group_stride_bytes) {
   uint64_t d = 0;
@@ -74,7 +76,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t ring_a = (raw + 1023u) & ~1023u;
   const uint32_t a_stage = (uint32_t)P * p.patch_bytes, b_stage = (uint32_t)P * kBBytes;
   const uint32_t ring_b = ring_a + (uint32_t)p.stages_a * a_stage;
-  uint8_t *ctrl = smem_raw + (ring_b - raw) + (size_t)p.stages_b * b_stage;
+  uint8_t *stage_buf = smem_raw + (ring_b - raw) + (size_t)p.stages_b * b_stage;   // epilogue store staging
+  uint8_t *ctrl = stage_buf + kStageBytes;
   const uint32_t fullA = smem_u32(ctrl), emptyA = fullA + 8 * kMaxStages;
   const uint32_t fullB = emptyA + 8 * kMaxStages, emptyB = fullB + 8 * kMaxStages;
   const uint32_t tfull0 = emptyB + 8 * kMaxStages, tempty0 = tfull0 + 16;
@@ -240,11 +243,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ok = y < p.H && x < p.W;
       }
       const long long pix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+      // coalesced plane stores: the warp's 32-pixel x 32-channel block is transposed through shared memory so
+      // that 4 consecutive lanes write the 64 contiguous bytes of one pixel (full 32-B sectors) instead of every
+      // lane writing 16 B of its own pixel.  Lane l stores for pixels (l >> 2) + 8 * it, 16-byte chunk l & 3.
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      long long spix[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long hi = __shfl_sync(0xffffffffu, (int)(pix >> 32), it * 8 + (lane >> 2));
+        const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(pix & 0xffffffffll), it * 8 + (lane >> 2));
+        spix[it] = (hi << 32) | lo;
+      }
+      uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 2) * 32 * kStagePitch);
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = 0; chunk < ((p.debug & 16) ? 0 : BN / 32); ++chunk) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
         tmem_ld_wait();
@@ -279,26 +294,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], p.TW));
           }
         }
-        if (ok && c0 < p.Cout && !(p.debug & 8)) {
+        if (!out_f32) {
+          for (int pl = 0; pl < P; ++pl) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+              w[i] = pack_bf16x2(h0, h1);
+              v[2 * i] = __fsub_rn(v[2 * i], __bfloat162float(h0));       // exact residual for the next plane
+              v[2 * i + 1] = __fsub_rn(v[2 * i + 1], __bfloat162float(h1));
+            }
+            __syncwarp();     // previous readers of the staging block are done
+#pragma unroll
+            for (int q = 0; q < 4; ++q) stage_w[lane * (kStagePitch / 16) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            __syncwarp();
+            if (c0 < p.Cout && !(p.debug & 8)) {
+              __nv_bfloat16 *obase = reinterpret_cast<__nv_bfloat16 *>(p.out) + (long long)pl * p.out_plane_stride + c0 + (lane & 3) * 8;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int pp = it * 8 + (lane >> 2);
+                const uint4 val = stage_w[pp * (kStagePitch / 16) + (lane & 3)];
+                if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout) = val;
+              }
+            }
+          }
+        } else if (ok && c0 < p.Cout && !(p.debug & 8)) {
           if (out_f32) {
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.Cout + c0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + pix * p.Cout + c0;
-            for (int pl = 0; pl < P; ++pl) {
-              uint32_t w[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-                w[i] = pack_bf16x2(h0, h1);
-                v[2 * i] = __fsub_rn(v[2 * i], __bfloat162float(h0));       // exact residual for the next plane
-                v[2 * i + 1] = __fsub_rn(v[2 * i + 1], __bfloat162float(h1));
-              }
-              uint4 *dst = reinterpret_cast<uint4 *>(o + (long long)pl * p.out_plane_stride);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-            }
           }
         }
       }
@@ -327,7 +351,7 @@ static int env_int(const char *name, int dflt) {
 template <int BN, int P, int TAPS>
 static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
   const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
-  const size_t budget = 227 * 1024 - 1024 - kCtrlBytes;
+  const size_t budget = 227 * 1024 - 1024 - kCtrlBytes - kStageBytes;
   // activation ring: two stages when they leave room for at least two weight stages, else one
   int sa = (2 * a_stage + 2 * b_stage <= budget) ? 2 : 1;
   if (p.taps == 1) sa = (int)std::min<size_t>(4, std::max<size_t>(1, (budget / 2) / a_stage));
@@ -338,7 +362,7 @@ static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams 
   sb = std::max(1, std::min(sb, env_int("CTPN_TC_STAGES_B", sb)));
   p.stages_a = sa;
   p.stages_b = sb;
-  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kCtrlBytes;
+  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kStageBytes + kCtrlBytes;
   CTPN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, P, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   char label[128];
@@ -400,9 +424,9 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
 
   // N tile: 256 halves the A traffic per MAC but, with two accumulators per tile (P > 1), leaves no TMEM for
   // double buffering -- worth it only when the K loop is long enough to amortise the serialised epilogue.
-  int BN = env_int("CTPN_TC_BN", (planes == 1 || (planes == 2 && taps * cin >= 9 * 256)) ? 256 : 128);
+  int BN = env_int("CTPN_TC_BN", planes == 1 ? 256 : 128);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
-  if (planes == 3 && BN > 128) BN = 128;   // three planes of a 256-wide weight tile do not fit the stage budget
+  if (planes > 1 && BN > 128) BN = 128;   // main + cross accumulators, double buffered: 4 * BN TMEM columns <= 512
   while (BN > cout || cout % BN) BN >>= 1;
   p.tiles_n = cout / BN;
   p.nbuf = ((planes > 1 ? 2 : 1) * BN * 2 <= 512) ? 2 : 1;   // 512 TMEM columns per SM

@@ -197,7 +197,7 @@ class Engine:
             copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream()
 
-        bufs = {}          # two persistent device input buffers, used alternately
+        bufs = self.__dict__.setdefault("_stream_bufs", {})   # two persistent device input buffers, used alternately
         done = [None, None]  # event: compute that read buffer i has been enqueued and finished
         counter = [0]
 
