@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--planes", type=int, default=int(os.environ.get("CTPN_BENCH_PLANES", "2")))
     ap.add_argument("--height", type=int, default=600)
     ap.add_argument("--width", type=int, default=900)
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("CTPN_BENCH_STREAMS", "1")), help="sub-batch streams per GPU")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images in the cpu_baseline sample")
     return ap.parse_args()
 
@@ -156,7 +157,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, H, W, K = a.batch, a.height, a.width, a.steps
-    eng = Engine(synth.make_weights(0), planes=a.planes, device=local)
+    eng = Engine(synth.make_weights(0), planes=a.planes, device=local, streams=a.streams)
     rs = np.random.RandomState(100 + rank)
     host = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
     host.numpy()[...] = rs.randint(0, 256, size=(B, H, W, 3), dtype=np.uint8)
@@ -239,7 +240,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "batch=%d/GPU %dx%dx3 uint8 synthetic, random-init VGG16+BiLSTM+heads (seed 0), proposal layer "
                                    "(12000 pre / 1000 post NMS), DETECT_MODE H; output = test_ctpn() rois" % (B, H, W),
-                       "global_batch": world * B, "planes": a.planes, "parallelism": "dp%d (independent image shards, NCCL all-gather of rois)" % world,
+                       "global_batch": world * B, "planes": a.planes, "streams": a.streams, "parallelism": "dp%d (independent image shards, NCCL all-gather of rois)" % world,
                        "l2": "no explicit flush: every step streams >4 GB of activations through the 126 MB L2, nothing survives between steps"},
             "e2e": {"value": world * B * K / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 + B * 12,
                     "d2h_bytes_per_step": B * post * 5 * 4 + B * 4},

@@ -37,8 +37,13 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
   const int groups = (R + RG - 1) / RG;
   const int dir = cid / groups, row0 = (cid % groups) * RG;
   const int t = threadIdx.x;
-  const int g = t >> 6, ul = t & 63;                     // gate, local unit of this thread's column
-  const int gcol = g * kHid + rank * kHalf + ul;         // column in the 512-wide gate vector
+  // mat-vec phase: thread = 4 adjacent local columns x RG/4 rows (register tile: 4 + RG/4 shared-memory loads
+  // per 4 * RG/4 * 4 FMAs); cell phase: thread = unit ul, rows (t >> 6) + 4q
+  constexpr int RT = RG / 4;
+  const int cg = t & 63, rg = t >> 6;                    // column group (4 columns), row group (RT rows)
+  const int lc0 = cg * 4;                                // first local column; gate = lc0 >> 6, unit = lc0 & 63
+  const int gcol0 = (lc0 >> 6) * kHid + rank * kHalf + (lc0 & 63);   // column in the 512-wide gate vector
+  const int ul = t & 63;
   const float *wh = dir ? wh_bw : wh_fw;
   for (int i = t; i < kHid * kLocalCols; i += 256) {
     const int k = i >> 8, lc = i & 255;
@@ -57,28 +62,33 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
     const float *hc = hbuf + (step & 1) * RG * kHid;
     float *hn = hbuf + ((step + 1) & 1) * RG * kHid;
     float *hn_peer = peer_h + ((step + 1) & 1) * RG * kHid;
-    float xp[RG], acc[RG];
+    float4 acc[RT];
 #pragma unroll
-    for (int r = 0; r < RG; ++r) {
-      const int row = row0 + r;
-      xp[r] = row < R ? __ldg(xproj + ((long long)row * W + tpos) * (2 * kGates) + dir * kGates + gcol) : 0.f;
-      acc[r] = 0.f;
+    for (int r = 0; r < RT; ++r) {
+      const int row = row0 + rg * RT + r;
+      acc[r] = row < R ? __ldg(reinterpret_cast<const float4 *>(xproj + ((long long)row * W + tpos) * (2 * kGates) + dir * kGates + gcol0))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll 2
     for (int k = 0; k < kHid; k += 4) {
-      const float w0 = Ws[(k + 0) * kLocalCols + t], w1 = Ws[(k + 1) * kLocalCols + t];
-      const float w2 = Ws[(k + 2) * kLocalCols + t], w3 = Ws[(k + 3) * kLocalCols + t];
+      float4 w[4];
 #pragma unroll
-      for (int r = 0; r < RG; ++r) {
-        const float4 h4 = *reinterpret_cast<const float4 *>(hc + r * kHid + k);
-        acc[r] = fmaf(h4.x, w0, acc[r]);
-        acc[r] = fmaf(h4.y, w1, acc[r]);
-        acc[r] = fmaf(h4.z, w2, acc[r]);
-        acc[r] = fmaf(h4.w, w3, acc[r]);
+      for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kLocalCols + lc0);
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const float4 h4 = *reinterpret_cast<const float4 *>(hc + (rg * RT + r) * kHid + k);
+        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[r].x = fmaf(hv[kk], w[kk].x, acc[r].x);
+          acc[r].y = fmaf(hv[kk], w[kk].y, acc[r].y);
+          acc[r].z = fmaf(hv[kk], w[kk].z, acc[r].z);
+          acc[r].w = fmaf(hv[kk], w[kk].w, acc[r].w);
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RG; ++r) gates[r * kLocalCols + t] = xp[r] + acc[r];
+    for (int r = 0; r < RT; ++r) *reinterpret_cast<float4 *>(gates + (rg * RT + r) * kLocalCols + lc0) = acc[r];
     __syncthreads();
     // cell update: thread -> unit ul, rows (t>>6) + 4q
 #pragma unroll

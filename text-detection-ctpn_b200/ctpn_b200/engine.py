@@ -24,7 +24,7 @@ DEFAULT_CFG = dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THR
 
 
 class Engine:
-    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False):
+    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False, streams=1):
         if not torch.cuda.is_available():
             raise N.CtpnError("ctpn_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -43,6 +43,8 @@ class Engine:
             N.check(N.lib.ctpn_net_set_option(self._net, b"keep_activations", 1), "set_option")
         self._ws = {}
         self._pinned = {}
+        self.streams = int(streams)
+        self._side = []
         if weights is not None:
             self.load_weights(weights)
 
@@ -86,7 +88,7 @@ class Engine:
         return fh.value, fw.value
 
     # ---- stages ----------------------------------------------------------------------------
-    def forward_heads(self, images):
+    def forward_heads(self, images, ws_key="net"):
         """images: CUDA tensor [B,H,W,3], uint8 BGR (mean subtraction fused) or float32 blob
         (already mean-subtracted, test.py:9).  Returns (rpn_cls_score [B,h,w,20] logits,
         rpn_bbox_pred [B,h,w,40]) float32 CUDA tensors."""
@@ -96,7 +98,7 @@ class Engine:
         B, H, W, _ = images.shape
         fh, fw = self.feature_hw(H, W)
         need = N.lib.ctpn_net_workspace_bytes(self._net, B, H, W)
-        ws = self._workspace("net", need)
+        ws = self._workspace(ws_key, need)
         cls = torch.empty((B, fh, fw, 20), dtype=torch.float32, device=self.device)
         bbox = torch.empty((B, fh, fw, 40), dtype=torch.float32, device=self.device)
         N.check(N.lib.ctpn_net_forward(self._net, N.ptr(images), int(is_f32), B, H, W, N.ptr(cls), N.ptr(bbox),
@@ -111,7 +113,7 @@ class Engine:
         N.check(N.lib.ctpn_net_debug_tap(self._net, name.encode(), N.ptr(out), out.numel(), C.byref(cnt), N.stream_ptr()), "debug_tap")
         return out
 
-    def proposals(self, cls, bbox, im_info, cls_is_logit=True, cfg=None):
+    def proposals(self, cls, bbox, im_info, cls_is_logit=True, cfg=None, ws_key="prop"):
         """Batched proposal layer (proposal_layer_tf.py:14-157) on CUDA tensors.
         Returns rois [B,post,5] (score,x1,y1,x2,y2), index [B,post] int32, count [B] int32."""
         c = dict(self.cfg)
@@ -123,7 +125,7 @@ class Engine:
         max_n = pre if 0 < pre < NA else NA
         rows = post if post > 0 else max_n
         need = N.lib.ctpn_proposals_workspace_bytes(B, H, W, pre)
-        ws = self._workspace("prop", need)
+        ws = self._workspace(ws_key, need)
         rois = torch.empty((B, rows, 5), dtype=torch.float32, device=self.device)
         index = torch.empty((B, rows), dtype=torch.int32, device=self.device)
         count = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -138,9 +140,30 @@ class Engine:
     def detect_device(self, images, im_info):
         """images: CUDA [B,H,W,3] uint8/float32; im_info: [B,3] tensor (blob_h, blob_w, scale).
         Returns device tensors (rois [B,post,5], count [B])."""
-        cls, bbox = self.forward_heads(images)
-        rois, _, count = self.proposals(cls, bbox, im_info, cls_is_logit=True)
-        return rois, count
+        n = min(self.streams, images.shape[0])
+        if n <= 1:
+            cls, bbox = self.forward_heads(images)
+            rois, _, count = self.proposals(cls, bbox, im_info, cls_is_logit=True)
+            return rois, count
+        # sub-batches on side streams: the SIMT kernels of one sub-batch (conv1_1, BiLSTM, sort, NMS) run beside
+        # the tensor-core kernels of the other (a persistent conv CTA leaves room for them on every SM)
+        main = torch.cuda.current_stream()
+        if len(self._side) < n:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        im_info = im_info.to(self.device)
+        bounds = [images.shape[0] * i // n for i in range(n + 1)]
+        parts = []
+        for i in range(n):
+            st = self._side[i]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                sub = images[bounds[i]:bounds[i + 1]]
+                cls, bbox = self.forward_heads(sub, ws_key="net%d" % i)
+                r, _, c = self.proposals(cls, bbox, im_info[bounds[i]:bounds[i + 1]], cls_is_logit=True, ws_key="prop%d" % i)
+                parts.append((r, c))
+        for st in self._side[:n]:
+            main.wait_stream(st)
+        return torch.cat([r for r, _ in parts]), torch.cat([c for _, c in parts])
 
     def all_gather(self, rois, count):
         """Multi-GPU (one process per GPU, torch.distributed/NCCL initialised by the caller): every rank
