@@ -98,6 +98,11 @@ int ctpn_pack_weights(const float *w_tf, int taps, int cin, int cout, int cout_p
 int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, const float *w_hwio,
                  const float *bias, void *out_planes, int B, int H, int W, int planes, void *stream);
 
+/* Same layer on the tensor cores: the im2col tile (K = 27 padded to 32) is built in shared memory as bf16
+ * planes and multiplied by the resident weight tile with tcgen05.mma; HBM-write bound.  Default in ctpn_net_forward. */
+int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const float *w_hwio,
+                    const float *bias, void *out_planes, int B, int H, int W, int planes, void *stream);
+
 /* 3x3 SAME conv (taps=9) or 1x1 / matmul (taps=1) on planes with tcgen05 tensor cores.
  * flags: bit0 ReLU, bit1 fused 2x2/2 VALID max-pool (taps=9 only), bit2 float32 output
  * [B][H][W][Cout] instead of planes.  Cin % 64 == 0, Cout % 64 == 0. */
@@ -124,7 +129,7 @@ int ctpn_net_create(ctpn_net_t **net, int planes);
 int ctpn_net_destroy(ctpn_net_t *net);
 /* options: "keep_activations" (1: every layer gets its own workspace region so that
  * ctpn_net_debug_tap can read all of them after a forward), "conv_simt" (1: run the float32 SIMT
- * reference kernels instead of the tcgen05 path). */
+ * reference kernels instead of the tcgen05 path), "conv1_simt" (1: float32 SIMT conv1_1 only). */
 int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value);
 /* name = TF variable name; data = host float32 in TF layout. */
 int ctpn_net_set_weight(ctpn_net_t *net, const char *name, const float *data_host, size_t count);

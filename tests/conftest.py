@@ -13,3 +13,12 @@ for p in (PKG, ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def pytest_sessionstart(session):
+    # the CPU oracle runs on torch-CPU: more than ~32 threads is much slower on many-core hosts
+    try:
+        import torch
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+    except Exception:
+        pass

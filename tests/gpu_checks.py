@@ -86,6 +86,34 @@ def cmd_conv(a):
     return 0 if ok else 1
 
 
+def cmd_conv1(a):
+    """conv1_1 (tensor-core im2col-in-smem kernel or the SIMT one) against float64 on the same uint8 image."""
+    import torch
+    from ctpn_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    rs = np.random.RandomState(a.seed)
+    im = rs.randint(0, 256, size=(a.B, a.H, a.W, 3)).astype(np.uint8)
+    w = (rs.standard_normal((3, 3, 3, 64)) * (2.0 / 27) ** 0.5 / 75.0).astype(np.float32)
+    b = (rs.standard_normal(64) * 0.1).astype(np.float32)
+    means = np.array([102.9801, 115.9465, 122.7717])
+    lut = (np.arange(256, dtype=np.float64)[:, None] - means[None, :]).astype(np.float32)
+    imd, wd, bd, lutd = (torch.from_numpy(x).to(dev) for x in (im, w, b, lut))
+    out = torch.zeros((a.planes, a.B, a.H, a.W, 64), dtype=torch.bfloat16, device=dev)
+    fn = N.lib.ctpn_conv1_1 if a.impl == "simt" else N.lib.ctpn_conv1_1_tc
+    N.check(fn(N.ptr(imd), 0, N.ptr(lutd), N.ptr(wd), N.ptr(bd), N.ptr(out), a.B, a.H, a.W, a.planes, N.stream_ptr()), "conv1_1")
+    torch.cuda.synchronize()
+    got = out.double().sum(0)
+    x = torch.from_numpy(lut.astype(np.float64)[im.reshape(-1, 3), np.arange(3)].reshape(im.shape)).to(dev).permute(0, 3, 1, 2)
+    wr = torch.from_numpy(w.astype(np.float64)).to(dev).permute(3, 2, 0, 1)
+    y = torch.relu(torch.nn.functional.conv2d(x, wr, bd.double(), padding=1)).permute(0, 2, 3, 1)
+    err = (got - y).abs().max().item()
+    scale = y.abs().max().item()
+    tol = {1: 1.2e-2, 2: 6e-5, 3: 3e-6}[a.planes] if a.impl != "simt" else {1: 4e-3, 2: 2e-5, 3: 2e-6}[a.planes]
+    ok = bool(torch.isfinite(got).all().item()) and err <= tol * scale
+    print(json.dumps(dict(ok=ok, max_err=err, scale=scale, rel=err / scale, tol=tol)))
+    return 0 if ok else 1
+
+
 def cmd_bilstm(a):
     import torch
     from ctpn_b200 import _native as N
@@ -125,11 +153,15 @@ def main():
     for k, d in dict(B=1, H=8, W=16, cin=64, cout=64, taps=9, planes=1, flags=0, seed=0, nonneg=0).items():
         c.add_argument("--" + k, type=int, default=d)
     c.add_argument("--impl", default="tc")
+    c1 = sub.add_parser("conv1")
+    for k, d in dict(B=1, H=37, W=45, planes=2, seed=0).items():
+        c1.add_argument("--" + k, type=int, default=d)
+    c1.add_argument("--impl", default="tc")
     l = sub.add_parser("bilstm")
     for k, d in dict(R=37, W=56, planes=2, seed=0).items():
         l.add_argument("--" + k, type=int, default=d)
     a = ap.parse_args()
-    return {"conv": cmd_conv, "bilstm": cmd_bilstm}[a.cmd](a)
+    return {"conv": cmd_conv, "conv1": cmd_conv1, "bilstm": cmd_bilstm}[a.cmd](a)
 
 
 if __name__ == "__main__":

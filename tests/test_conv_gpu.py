@@ -67,3 +67,9 @@ def test_conv_simt_reference(case):
 @pytest.mark.parametrize("R,W,planes", [(37, 56, 2), (5, 7, 3), (1184, 56, 1), (600, 100, 2)])
 def test_bilstm_recurrence(R, W, planes):
     run_check("bilstm", "--R", R, "--W", W, "--planes", planes)
+
+
+@pytest.mark.parametrize("B,H,W,planes,impl", [(2, 37, 45, 2, "tc"), (1, 16, 8, 1, "tc"), (1, 50, 70, 3, "tc"), (1, 600, 900, 2, "tc"),
+                                               (2, 37, 45, 2, "simt"), (1, 50, 70, 3, "simt")])
+def test_conv1_1(B, H, W, planes, impl):
+    run_check("conv1", "--B", B, "--H", H, "--W", W, "--planes", planes, "--impl", impl)

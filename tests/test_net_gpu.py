@@ -154,3 +154,53 @@ def test_batch_equals_singles_and_simt_cross_check(weights):
     d = max(float((c1 - c2).abs().max()), float((b1 - b2).abs().max()))
     print('tcgen05 vs SIMT head diff %.2e' % d)
     assert d < 5e-4
+
+
+def test_config4_high_resolution_1200x1600(weights):
+    """BASELINE.json configs[3]: 1200x1600 images (75x100 feature map, 75 000 anchors, 12 000 into NMS).
+    Uses the engine API directly (the reference's test_ctpn would first shrink the image to 600x800 unless
+    cfg.TEST.SCALES / MAX_SIZE are overridden)."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, planes=2)
+    ims = np.stack([synth.make_image(40 + i, 1200, 1600) for i in range(2)])
+    info = np.array([[1200, 1600, 1.0]] * 2, np.float32)
+    rois = eng.rois_batch(ims, info)
+    blob = (ims[0].astype(np.float32) - net_cpu.PIXEL_MEANS.astype(np.float64)).astype(np.float32)[None]
+    ref = net_cpu.forward(blob, weights)
+    assert ref["rpn_cls_score"].shape == (1, 75, 100, 20)
+    want, _ = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info[:1])
+    got = rois[0]
+    assert got.shape[0] == 1000 and want.shape[0] == 1000
+    k = 100                                                   # strongest proposals: far from sort/NMS decision boundaries
+    np.testing.assert_allclose(got[:k, 0], want[:k, 0], atol=1e-3)
+    found = 0
+    for r in want[:k]:
+        d = np.abs(got[:, 1:] - r[1:]).max(axis=1)
+        found += bool((d <= 1e-3 * np.maximum(1.0, np.abs(r[1:]).max())).any())
+    assert found >= 0.97 * k, found
+
+
+def test_config5_mixed_shapes_oriented_connector(weights):
+    """BASELINE.json configs[4]: a mix of 600x900 and 900x600 images (two shape buckets) through the
+    reference call sequence with DETECT_MODE 'O' (oriented text-line connector)."""
+    from ctpn_b200 import Session
+    from lib.fast_rcnn.config import cfg
+    from lib.fast_rcnn.test import test_ctpn
+    from lib.networks.factory import get_network
+    from lib.text_connector.detectors import TextDetector
+    from oracle import textline
+    sess = Session(weights, planes=2)
+    net = get_network("VGGnet_test")
+    old = cfg.TEST.DETECT_MODE
+    cfg.TEST.DETECT_MODE = "O"
+    try:
+        for seed, (h, w) in [(50, (600, 900)), (51, (900, 600)), (52, (600, 900))]:
+            im = synth.make_image(seed, h, w)
+            scores, boxes = test_ctpn(sess, net, im)
+            assert boxes.shape[0] == scores.shape[0] > 0
+            assert boxes[:, [0, 2]].max() <= w - 1 and boxes[:, [1, 3]].max() <= h - 1
+            lines = TextDetector().detect(boxes, scores[:, np.newaxis], im.shape[:2])
+            want = textline.detect(boxes, scores[:, np.newaxis], im.shape[:2], mode="O")   # same proposals -> same lines
+            np.testing.assert_array_equal(lines, want)
+    finally:
+        cfg.TEST.DETECT_MODE = old

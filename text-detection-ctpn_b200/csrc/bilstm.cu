@@ -136,7 +136,9 @@ extern "C" int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, con
   CTPN_REQUIRE(R > 0 && W > 0, "ctpn_bilstm_recurrent: bad shape R=%d W=%d", R, W);
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_bilstm_recurrent: planes must be 1..3");
   cudaStream_t st = (cudaStream_t)stream;
-  if (R >= 16 * 74) return launch_bilstm<16>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
-  if (R >= 8 * 74) return launch_bilstm<8>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  // rows per cluster: as many as keeps every SM busy in a single wave (148 SMs = 74 clusters per direction pair)
+  if (R >= 32 * 37) return launch_bilstm<32>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 16 * 37) return launch_bilstm<16>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 8 * 37) return launch_bilstm<8>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
   return launch_bilstm<4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
 }

@@ -1,0 +1,293 @@
+// conv1_1 on the tensor cores: 3 -> 64 channels, K = 27 (padded to 32), uint8 / float32 image in, bf16 planes out.
+//
+// The layer is HBM-write bound (3 B in, 64 * P * 2 B out per pixel); the float32 SIMT version (conv_simt.cu) spends
+// 1728 FMAs per pixel and reaches only a third of that bound.  Here the im2col tile is built IN SHARED MEMORY:
+//   * 4 builder warps (thread = pixel of a 16 x 8 patch) gather the 27 mean-subtracted inputs of their pixel from a
+//     small staged image patch, split them into P bf16 planes and write one K-major 128-byte row per plane in the
+//     128B-swizzled UMMA layout (only the first 64 bytes = 32 k-values are ever read),
+//   * one thread issues 2 (k-slices) x {1,3,6} (plane pairs) tcgen05.mma of shape 128 x 64 x 16 per tile against the
+//     CTA-resident weight tile (built once from the float32 HWIO weights),
+//   * 4 epilogue warps do bias + ReLU + plane split and store through the same shared-memory transpose as conv_tc.
+// Accumulators (main + cross, see conv_tc.cu) are double buffered in TMEM; the A tile is double buffered in smem.
+// Numerics: operands carry P bf16 planes like every other tensor-core layer (planes=3 is float32-equivalent).
+// Reference semantics: lib/networks/network.py:160-183 (conv1_1), lib/fast_rcnn/test.py:8-9 (mean subtraction).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ctpn {
+
+constexpr int kC1tThreads = 288;          // warp 0: MMA issuer / TMEM owner, warps 1-4: builders, warps 5-8: epilogue
+constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
+constexpr int kC1tStagePitch = 80;
+
+struct Conv1TcParams {
+  const void *src;
+  const float *lut, *w, *bias;
+  __nv_bfloat16 *out;
+  int B, H, W, src_is_f32;
+  int tiles_x, tiles_y, total_tiles;
+  long long plane_stride;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kC1tThreads, 1)
+conv1_tc_kernel(const Conv1TcParams p) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a0 = (raw + 1023u) & ~1023u;                 // A tiles: [2 stages][P planes][16 KB]
+  const uint32_t b0 = a0 + 2u * P * kC1tTileBytes;            // weights: [P planes][64 rows x 128 B]
+  uint8_t *base = smem_raw + (a0 - raw);
+  uint8_t *bsm = base + 2 * P * kC1tTileBytes;
+  float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);          // [2 stages][18][10][3] floats
+  uint8_t *stage_buf = reinterpret_cast<uint8_t *>(patch + 2 * 18 * 10 * 3);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 4 * 32 * kC1tStagePitch);
+  const uint32_t fullA = smem_u32(bars), emptyA = fullA + 16, tfull = fullA + 32, tempty = fullA + 48;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(fullA + 8 * i, 128);     // every builder thread arrives
+      mbar_init(emptyA + 8 * i, 1);      // tcgen05.commit
+      mbar_init(tfull + 8 * i, 1);
+      mbar_init(tempty + 8 * i, 4);
+    }
+    fence_mbar_init();
+  }
+  constexpr uint32_t acc_cols = (P > 1 ? 2u : 1u) * 64u;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
+    tmem_relinquish();
+  }
+  // resident weight tile: row = cout, k-major, bf16 planes, 128B swizzle (chunk ^= row & 7); k >= 27 is zero
+  for (int i = threadIdx.x; i < 64 * 4; i += kC1tThreads) {
+    const int co = i >> 2, chunk = i & 3;
+    uint32_t pk[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = chunk * 8 + j * 2 + e;
+        v[e] = k < 27 ? p.w[k * 64 + co] : 0.f;
+      }
+      __nv_bfloat16 h0[3], h1[3];
+      split_planes(v[0], P, h0);
+      split_planes(v[1], P, h1);
+#pragma unroll
+      for (int pl = 0; pl < P; ++pl) pk[pl][j] = pack_bf16x2(h0[pl], h1[pl]);
+    }
+#pragma unroll
+    for (int pl = 0; pl < P; ++pl)
+      *reinterpret_cast<uint4 *>(bsm + pl * 64 * 128 + co * 128 + ((chunk ^ (co & 7)) << 4)) = make_uint4(pk[pl][0], pk[pl][1], pk[pl][2], pk[pl][3]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t kIdesc = umma_idesc_bf16(128, 64);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    int s = 0, a = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty + 8 * a, aph ^ 1u);
+      mbar_wait(fullA + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t a_lo = (((a0 + s * P * kC1tTileBytes) >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo = ((b0 >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t d_main = tmem_base + (uint32_t)a * acc_cols, d_cross = d_main + 64;
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+          for (int j = 0; j < P - i; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {   // K = 32 (27 real taps): two 16-wide slices
+              const uint64_t da = ((uint64_t)kHi << 32) | (a_lo + i * (kC1tTileBytes >> 4) + 2u * k);
+              const uint64_t db = ((uint64_t)kHi << 32) | (b_lo + j * ((64 * 128) >> 4) + 2u * k);
+              if (i + j == 0) mma_bf16_ss(d_main, da, db, kIdesc, k);
+              else mma_bf16_ss(d_cross, da, db, kIdesc, (k == 0 && i == 0 && j == 1) ? 0u : 1u);
+            }
+        mma_commit(emptyA + 8 * s);
+        mma_commit(tfull + 8 * a);
+      }
+      __syncwarp();
+      if (++s == 2) { s = 0; ph ^= 1u; }
+      if (++a == 2) { a = 0; aph ^= 1u; }
+    }
+  } else if (warp <= 4) {
+    // ===== im2col builders: thread = pixel m of the 16 x 8 patch =====
+    const int m = (warp - 1) * 32 + lane, th = m >> 3, tw = m & 7;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
+      const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+      float *pt = patch + s * (18 * 10 * 3);
+      mbar_wait(emptyA + 8 * s, ph ^ 1u);     // MMAs that read this stage (and its patch) are done
+      // stage the 18 x 10 x 3 mean-subtracted input patch (zero outside the image: SAME padding of the blob)
+      for (int i = m; i < 18 * 10 * 3; i += 128) {
+        const int c = i % 3, xx = (i / 3) % 10, yy = i / 30;
+        const int gx = x0 + xx - 1, gy = y0 + yy - 1;
+        float v = 0.f;
+        if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
+          const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3 + c;
+          v = p.src_is_f32 ? reinterpret_cast<const float *>(p.src)[off]
+                           : p.lut[reinterpret_cast<const uint8_t *>(p.src)[off] * 3 + c];
+        }
+        pt[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // builder warps only
+      uint8_t *arow = base + s * P * kC1tTileBytes + m * 128;
+#pragma unroll
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t pk[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = chunk * 8 + j * 2 + e;       // k = (ky * 3 + kx) * 3 + c
+            v[e] = k < 27 ? pt[((th + k / 9) * 10 + tw + (k / 3) % 3) * 3 + k % 3] : 0.f;
+          }
+          __nv_bfloat16 h0[3], h1[3];
+          split_planes(v[0], P, h0);
+          split_planes(v[1], P, h1);
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) pk[pl][j] = pack_bf16x2(h0[pl], h1[pl]);
+        }
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl)
+          *reinterpret_cast<uint4 *>(arow + pl * kC1tTileBytes + ((chunk ^ (m & 7)) << 4)) = make_uint4(pk[pl][0], pk[pl][1], pk[pl][2], pk[pl][3]);
+      }
+      fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(fullA + 8 * s);
+      if (++s == 2) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ===== epilogue warps 5..8 (TMEM lane quarter = warp & 3) =====
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane, th = m >> 3, tw = m & 7;
+    uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 5) * 32 * kC1tStagePitch);
+    int a = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
+      const int y = (r / p.tiles_x) * 16 + th, x = (r % p.tiles_x) * 8 + tw;
+      const bool ok = y < p.H && x < p.W;
+      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      long long spix[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long hi = __shfl_sync(0xffffffffu, (int)(pix >> 32), it * 8 + (lane >> 2));
+        const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(pix & 0xffffffffll), it * 8 + (lane >> 2));
+        spix[it] = (hi << 32) | lo;
+      }
+      mbar_wait(tfull + 8 * a, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
+#pragma unroll 1
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t rr[32];
+        tmem_ld_32x32(taddr + chunk * 32, rr);
+        tmem_ld_wait();
+        float v[32];
+        if (P > 1) {
+          uint32_t rc[32];
+          tmem_ld_32x32(taddr + 64 + chunk * 32, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + __uint_as_float(rc[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.bias + chunk * 32) + q);
+          v[4 * q + 0] = fmaxf(v[4 * q + 0] + bq.x, 0.f);
+          v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq.y, 0.f);
+          v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq.z, 0.f);
+          v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq.w, 0.f);
+        }
+        for (int pl = 0; pl < P; ++pl) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+            w[i] = pack_bf16x2(h0, h1);
+            v[2 * i] = __fsub_rn(v[2 * i], __bfloat162float(h0));
+            v[2 * i + 1] = __fsub_rn(v[2 * i + 1], __bfloat162float(h1));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) stage_w[lane * (kC1tStagePitch / 16) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          __syncwarp();
+          __nv_bfloat16 *obase = p.out + (long long)pl * p.plane_stride + chunk * 32 + (lane & 3) * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int pp = it * 8 + (lane >> 2);
+            const uint4 val = stage_w[pp * (kC1tStagePitch / 16) + (lane & 3)];
+            if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + 8 * a);
+      if (++a == 2) { a = 0; aph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * acc_cols);
+  }
+}
+
+template <int P>
+static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + 2 * 18 * 10 * 3 * sizeof(float) +
+                      4 * 32 * kC1tStagePitch + 64 + 16;
+  CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  CTPN_CUDA(cudaGetDevice(&dev));
+  CTPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  ProfScope prof("conv1_1", 2.0 * p.B * p.H * p.W * 27.0 * 64.0, st);
+  conv1_tc_kernel<P><<<grid, kC1tThreads, smem, st>>>(p);
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
+}  // namespace ctpn
+
+using namespace ctpn;
+
+extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                               void *out_planes, int B, int H, int W, int planes, void *stream) {
+  CTPN_REQUIRE(src && w_hwio && bias && out_planes, "ctpn_conv1_1_tc: null pointer");
+  CTPN_REQUIRE(src_is_f32 || lut, "ctpn_conv1_1_tc: uint8 input needs the mean-subtraction LUT");
+  CTPN_REQUIRE(B > 0 && H > 0 && W > 0, "ctpn_conv1_1_tc: bad shape");
+  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_conv1_1_tc: planes must be 1..3");
+  Conv1TcParams p;
+  p.src = src; p.lut = lut; p.w = w_hwio; p.bias = bias; p.out = (__nv_bfloat16 *)out_planes;
+  p.B = B; p.H = H; p.W = W; p.src_is_f32 = src_is_f32;
+  p.tiles_x = ceil_div(W, 8); p.tiles_y = ceil_div(H, 16);
+  const long long total = (long long)B * p.tiles_x * p.tiles_y;
+  CTPN_REQUIRE(total < (1ll << 31), "ctpn_conv1_1_tc: too many tiles");
+  p.total_tiles = (int)total;
+  p.plane_stride = (long long)B * H * W * 64;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (planes == 1) return launch_conv1_tc<1>(p, st);
+  if (planes == 2) return launch_conv1_tc<2>(p, st);
+  return launch_conv1_tc<3>(p, st);
+}

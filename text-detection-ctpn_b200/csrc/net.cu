@@ -31,7 +31,7 @@ using namespace ctpn;
 
 struct ctpn_net {
   int planes = 2;
-  int conv_simt = 0, keep = 0;
+  int conv_simt = 0, conv1_simt = 0, keep = 0;
   std::map<std::string, std::vector<float>> host;
   bool dirty = true;
   std::vector<void *> owned;
@@ -215,6 +215,7 @@ extern "C" int ctpn_net_create(ctpn_net_t **net, int planes) {
   ctpn_net *n = new ctpn_net();
   n->planes = planes;
   if (const char *e = getenv("CTPN_CONV_IMPL")) n->conv_simt = strcmp(e, "simt") == 0;
+  if (const char *e = getenv("CTPN_CONV1_IMPL")) n->conv1_simt = strcmp(e, "simt") == 0;
   *net = n;
   return CTPN_OK;
 }
@@ -230,6 +231,7 @@ extern "C" int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value) 
   CTPN_REQUIRE(net && key, "ctpn_net_set_option: null pointer");
   if (!strcmp(key, "keep_activations")) net->keep = value != 0;
   else if (!strcmp(key, "conv_simt")) net->conv_simt = value != 0;
+  else if (!strcmp(key, "conv1_simt")) net->conv1_simt = value != 0;
   else { set_error("ctpn_net_set_option: unknown key '%s'", key); return CTPN_ERR_INVALID; }
   return CTPN_OK;
 }
@@ -268,7 +270,8 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
   char *ws = (char *)workspace;
   const int P = net->planes;
   net->taps.clear();
-  if ((rc = ctpn_conv1_1(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, P, stream))) return rc;
+  auto conv1 = (net->conv_simt || net->conv1_simt) ? ctpn_conv1_1 : ctpn_conv1_1_tc;
+  if ((rc = conv1(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, P, stream))) return rc;
   net->taps["conv1_1"] = Tap{ws + L.act[0], (long long)B * H * W, 64, true};
   int h = H, w = W;
   for (int l = 1; l < 14; ++l) {

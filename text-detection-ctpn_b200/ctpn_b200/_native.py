@@ -41,6 +41,7 @@ SIGNATURES = {
     "ctpn_proposals": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p]),
     "ctpn_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "ctpn_conv1_1": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ctpn_conv1_1_tc": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ctpn_conv3x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ctpn_conv3x3_simt": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ctpn_bilstm_recurrent": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
