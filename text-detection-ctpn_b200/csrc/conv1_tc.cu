@@ -16,7 +16,7 @@
 
 namespace ctpn {
 
-constexpr int kC1tThreads = 288;          // warp 0: MMA issuer / TMEM owner, warps 1-4: builders, warps 5-8: epilogue
+constexpr int kC1tThreads = 416;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-12: epilogue
 constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
 constexpr int kC1tStagePitch = 80;
 
@@ -40,7 +40,8 @@ conv1_tc_kernel(const Conv1TcParams p) {
   uint8_t *base = smem_raw + (a0 - raw);
   uint8_t *bsm = base + 2 * P * kC1tTileBytes;
   float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);          // [2 stages][18][10][3] floats
-  uint8_t *stage_buf = reinterpret_cast<uint8_t *>(patch + 2 * 18 * 10 * 3);
+  float *lut_s = patch + 2 * 18 * 10 * 3;                                 // [256][3] mean-subtraction table
+  uint8_t *stage_buf = reinterpret_cast<uint8_t *>(lut_s + 768);
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 4 * 32 * kC1tStagePitch);
   const uint32_t fullA = smem_u32(bars), emptyA = fullA + 16, tfull = fullA + 32, tempty = fullA + 48;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
@@ -60,6 +61,8 @@ conv1_tc_kernel(const Conv1TcParams p) {
     tmem_alloc(smem_u32(tmem_slot), 2 * acc_cols);
     tmem_relinquish();
   }
+  if (!p.src_is_f32)
+    for (int i = threadIdx.x; i < 768; i += kC1tThreads) lut_s[i] = p.lut[i];
   // resident weight tile: row = cout, k-major, bf16 planes, 128B swizzle (chunk ^= row & 7); k >= 27 is zero
   for (int i = threadIdx.x; i < 64 * 4; i += kC1tThreads) {
     const int co = i >> 2, chunk = i & 3;
@@ -121,12 +124,14 @@ conv1_tc_kernel(const Conv1TcParams p) {
       if (++s == 2) { s = 0; ph ^= 1u; }
       if (++a == 2) { a = 0; aph ^= 1u; }
     }
-  } else if (warp <= 4) {
-    // ===== im2col builders: thread = pixel m of the 16 x 8 patch =====
-    const int m = (warp - 1) * 32 + lane, th = m >> 3, tw = m & 7;
-    int s = 0;
+  } else if (warp <= 8) {
+    // ===== im2col builders: two groups of 4 warps; group g owns stage g and builds every other tile of this CTA,
+    // so two tiles are in flight and the global-load latency of the patch staging is hidden.  thread = pixel m =====
+    const int grp = (warp - 1) >> 2;
+    const int m = ((warp - 1) & 3) * 32 + lane, th = m >> 3, tw = m & 7;
+    const int s = grp;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
       const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
       float *pt = patch + s * (18 * 10 * 3);
@@ -139,11 +144,12 @@ conv1_tc_kernel(const Conv1TcParams p) {
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
           const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3 + c;
           v = p.src_is_f32 ? reinterpret_cast<const float *>(p.src)[off]
-                           : p.lut[reinterpret_cast<const uint8_t *>(p.src)[off] * 3 + c];
+                           : lut_s[reinterpret_cast<const uint8_t *>(p.src)[off] * 3 + c];
         }
         pt[i] = v;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // builder warps only
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this builder group
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
       uint8_t *arow = base + s * P * kC1tTileBytes + m * 128;
 #pragma unroll
       for (int chunk = 0; chunk < 4; ++chunk) {
@@ -168,13 +174,13 @@ conv1_tc_kernel(const Conv1TcParams p) {
       }
       fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(fullA + 8 * s);
-      if (++s == 2) { s = 0; ph ^= 1u; }
+      ph ^= 1u;
     }
   } else {
-    // ===== epilogue warps 5..8 (TMEM lane quarter = warp & 3) =====
+    // ===== epilogue warps 9..12 (TMEM lane quarter = warp & 3) =====
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane, th = m >> 3, tw = m & 7;
-    uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 5) * 32 * kC1tStagePitch);
+    uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 9) * 32 * kC1tStagePitch);
     int a = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -255,7 +261,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
 
 template <int P>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + 2 * 18 * 10 * 3 * sizeof(float) +
+  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + (2 * 18 * 10 * 3 + 768) * sizeof(float) +
                       4 * 32 * kC1tStagePitch + 64 + 16;
   CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
