@@ -48,11 +48,11 @@ struct ConvTcParams {
   long long out_plane_stride;   // elements between output planes
 };
 
-constexpr int kTcThreads = 224;
+constexpr int kTcThreads = 352;   // warps: 0 B-producer, 1 MMA, 2-5 epilogue set 0, 6 A-producer, 7-10 epilogue set 1
 constexpr int kMaxStages = 8;
 constexpr int kCtrlBytes = 8 * (4 * kMaxStages + 4) + 16;
 constexpr int kStagePitch = 80;                    // bytes per pixel row of the epilogue staging buffer (64 B + 16 B pad)
-constexpr int kStageBytes = 4 * 32 * kStagePitch;  // one 32-pixel x 32-channel bf16 block per epilogue warp
+constexpr int kStageBytes = 8 * 32 * kStagePitch;  // one 32-pixel x 32-channel bf16 block per epilogue warp
 
 __device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_t group_stride_bytes) {
   uint64_t d = 0;
@@ -98,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);
+      mbar_init(tempty0 + 8 * a, 8);
     }
     fence_mbar_init();
   }
@@ -220,9 +220,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++a == p.nbuf) { a = 0; aph ^= 1u; }
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ===== epilogue warps (TMEM lane quarter = warp id % 4) =====
+  } else if (warp != 6) {
+    // ===== epilogue: two sets of four warps (TMEM lane quarter = warp id % 4); set 0 takes the even 32-column
+    // chunks of the accumulator, set 1 the odd ones =====
     const int quarter = warp & 3;
+    const int eset = warp >= 7 ? 1 : 0, ewarp = warp >= 7 ? warp - 3 : warp - 2;
     const int m = quarter * 32 + lane;
     const int th = m >> p.tw_log2, tw = m & (p.TW - 1);
     const bool pool = (p.flags & CTPN_F_POOL) != 0, relu = (p.flags & CTPN_F_RELU) != 0;
@@ -254,12 +256,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(pix & 0xffffffffll), it * 8 + (lane >> 2));
         spix[it] = (hi << 32) | lo;
       }
-      uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 2) * 32 * kStagePitch);
+      uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + ewarp * 32 * kStagePitch);
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
 #pragma unroll 1
-      for (int chunk = 0; chunk < ((p.debug & 16) ? 0 : BN / 32); ++chunk) {
+      for (int chunk = eset; chunk < ((p.debug & 16) ? 0 : BN / 32); chunk += 2) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
         tmem_ld_wait();
