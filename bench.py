@@ -252,6 +252,13 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         achieved = alg_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        traffic = None      # DRAM bytes of the 13 conv launches of one step, from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_traffic_planes%d.json" % a.planes)))
+            if tj.get("batch") == B and tj.get("planes") == a.planes and tj.get("launches") == 13:
+                traffic = tj["dram_bytes_per_step"]
+        except Exception:
+            pass
         mma_per_mac = {1: 1, 2: 3, 3: 6}[a.planes]
         tc_launches = int(sum(p["launches"] for p in conv + gemm))
         other_ms = {p["kernel"]: p["ms"] / K for p in prof if not p["kernel"].startswith("conv_tc")}
@@ -270,7 +277,7 @@ def main():
             "gpu_launches": K * KERNELS_PER_STEP_FIXED + tc_launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (13 tcgen05 3x3 conv launches per step)", "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per step over the 13 conv launches (ncu)",
                          "peak_source": peak_src, "ms_per_step": conv_ms,
                          "executed_mma_tflops": achieved * mma_per_mac,
                          "note": "achieved = algorithmic conv FLOPs (337.26 GFLOP/image) / CUDA-event time of the conv launches; with planes=%d "

@@ -204,3 +204,28 @@ def test_config5_mixed_shapes_oriented_connector(weights):
             np.testing.assert_array_equal(lines, want)
     finally:
         cfg.TEST.DETECT_MODE = old
+
+
+@pytest.mark.parametrize("h,w", [(50, 70), (16, 16), (33, 129)])
+def test_tiny_and_odd_image_sizes(weights, h, w):
+    """Ragged sizes: feature maps of 3x4, 1x1 and 2x8 cells; every pool level floors an odd dimension."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, planes=3)
+    im = synth.make_image(60 + h, h, w)
+    cls, bbox = eng.forward_heads(torch.from_numpy(im[None]).cuda())
+    blob = im.astype(np.float32)
+    blob -= net_cpu.PIXEL_MEANS
+    ref = net_cpu.forward(blob[None], weights, dtype=torch.float64)
+    assert tuple(cls.shape) == ref["rpn_cls_score"].shape
+    assert np.abs(cls.cpu().numpy() - ref["rpn_cls_score"]).max() < 1e-3
+    assert np.abs(bbox.cpu().numpy() - ref["rpn_bbox_pred"]).max() < 1e-3
+
+
+def test_errors_are_reported(weights):
+    from ctpn_b200 import CtpnError, Engine, _native as N
+    eng = Engine(None)
+    with pytest.raises(CtpnError, match="has not been set"):
+        eng.forward_heads(torch.zeros((1, 64, 64, 3), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(CtpnError):
+        eng.forward_heads(torch.zeros((1, 8, 64, 3), dtype=torch.uint8, device="cuda"))      # smaller than one cell
+    assert N.lib.ctpn_device_ok(99) != 0 and "device" in N.last_error()

@@ -70,5 +70,23 @@ def full(path):
         print("| %d | `%s` | %s |" % (i, name, " | ".join(cells)))
 
 
+def traffic(path, planes, batch):
+    """DRAM bytes (read + write) of every conv_tc 3x3 launch in an `ncu --set full` capture of ONE step -> JSON."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = []
+    for d in data:
+        if "conv_tc_kernel" not in d[hdr.index("Kernel Name")]:
+            continue
+        per.append({"read": float(d[ir]) * scale[units[ir]], "write": float(d[iw]) * scale[units[iw]],
+                    "ms": float(d[it]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "msecond": 1.0, "usecond": 1e-3}[units[it]]})
+    print(json.dumps({"planes": int(planes), "batch": int(batch), "launches": len(per),
+                      "dram_bytes_per_step": sum(q["read"] + q["write"] for q in per), "per_launch": per}))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
