@@ -229,3 +229,16 @@ def test_errors_are_reported(weights):
     with pytest.raises(CtpnError):
         eng.forward_heads(torch.zeros((1, 8, 64, 3), dtype=torch.uint8, device="cuda"))      # smaller than one cell
     assert N.lib.ctpn_device_ok(99) != 0 and "device" in N.last_error()
+
+
+def test_detect_list_buckets_mixed_shapes(weights):
+    from ctpn_b200 import Engine
+    eng = Engine(weights, planes=2)
+    shapes = [(64, 96), (96, 64), (64, 96), (48, 80), (96, 64)]
+    ims = [synth.make_image(70 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    res = eng.detect_list(ims, max_batch=2)
+    assert len(res) == len(ims)
+    for im, (s, b) in zip(ims, res):
+        s1, b1 = eng.detect(im)
+        np.testing.assert_array_equal(s, s1)
+        np.testing.assert_array_equal(b, b1)

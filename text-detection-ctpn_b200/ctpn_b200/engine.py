@@ -283,6 +283,23 @@ class Engine:
         info = np.array([[H, W, im_scale]] * B, np.float32)
         return [(r[:, 0], r[:, 1:5] / np.float32(im_scale)) for r in self.rois_batch(images, info)]
 
+    def detect_list(self, images, max_batch=32):
+        """Mixed-shape input (BASELINE.json configs[4]): a list of HxWx3 images of arbitrary sizes is grouped
+        into shape buckets, every bucket runs as batches of up to `max_batch`, and the (scores, boxes) results
+        come back in the order of the input list.  Images are taken at scale 1 (use test_ctpn for the
+        reference's rescaling rules)."""
+        buckets = {}
+        for i, im in enumerate(images):
+            buckets.setdefault((im.shape, im.dtype.str), []).append(i)
+        out = [None] * len(images)
+        for (_shape, _dt), idxs in buckets.items():
+            for k in range(0, len(idxs), max_batch):
+                part = idxs[k:k + max_batch]
+                res = self.detect_batch(np.stack([images[i] for i in part]))
+                for i, r in zip(part, res):
+                    out[i] = r
+        return out
+
     def detect(self, image, im_scale=1.0):
         """Single image [H,W,3] -> (scores, boxes); the test_ctpn() contract."""
         return self.detect_batch(image[None], im_scale)[0]
