@@ -85,7 +85,7 @@ def _load_reference_nms():
     return lib
 
 
-@pytest.mark.parametrize("n,thresh,ctpn_like", [(3000, 0.7, False), (12000, 0.7, True), (2000, 0.2, True)])
+@pytest.mark.parametrize("n,thresh,ctpn_like", [(3000, 0.7, False), (6000, 0.7, True), (2000, 0.2, True)])
 def test_against_the_reference_cuda_kernel(n, thresh, ctpn_like):
     """ctpn_nms_host vs the reference's `_nms` on identical sorted boxes.  The reference kernel is compiled with nvcc's
     default FMA contraction, so an IoU within 1 ulp of the threshold may decide differently; everything else must agree."""
