@@ -215,6 +215,16 @@ def main():
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
+    # single-image latency through the reference-shaped call (host image in, host rois out), 1 GPU only
+    lat_ms = None
+    if world == 1:
+        one = host[:1]
+        for _ in range(3):
+            eng.rois_batch(one)
+        t1 = time.perf_counter()
+        for _ in range(10):
+            eng.rois_batch(one)
+        lat_ms = (time.perf_counter() - t1) / 10 * 1e3
     n_props = float(sum(r.shape[0] for r in res)) / len(res)
 
     # secondary measurement (1 GPU only): the bf16 mode (planes=1, BASELINE.json configs[2] arithmetic); not the headline
@@ -284,6 +294,7 @@ def main():
                                  "each algorithmic MAC costs %d bf16 MMAs" % (a.planes, mma_per_mac)},
             "stage_ms_per_step": dict({"conv_tc 3x3 (13 launches)": conv_ms, "conv_tc 1x1 GEMMs (3 launches)": sum(p["ms"] for p in gemm) / K}, **other_ms),
             "proposals_per_image": n_props,
+            "single_image_latency_ms": lat_ms,
             "layers": [{"kernel": q["kernel"], "ms": q["ms"] / K, "alg_tflops": q["work"] / max(q["ms"], 1e-9) / 1e9} for q in conv + gemm],
         }
         if alt is not None:
