@@ -19,6 +19,7 @@ namespace ctpn {
 constexpr int kC1tThreads = 416;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-12: epilogue
 constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
 constexpr int kC1tStagePitch = 80;
+constexpr int kC1tPatch = 3 * 18 * 40;     // floats per staged input patch
 
 struct Conv1TcParams {
   const void *src;
@@ -39,8 +40,10 @@ conv1_tc_kernel(const Conv1TcParams p) {
   const uint32_t b0 = a0 + 2u * P * kC1tTileBytes;            // weights: [P planes][64 rows x 128 B]
   uint8_t *base = smem_raw + (a0 - raw);
   uint8_t *bsm = base + 2 * P * kC1tTileBytes;
-  float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);          // [2 stages][18][10][3] floats
-  float *lut_s = patch + 2 * 18 * 10 * 3;                                 // [256][3] mean-subtraction table
+  // input patch per stage: [3 channels][18 rows][40]: a row pitch of 40 floats makes the builders' gather
+  // (lanes = 4 tile rows x 8 tile columns) hit 32 distinct banks
+  float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);
+  float *lut_s = patch + 2 * kC1tPatch;                                 // [256][3] mean-subtraction table
   uint8_t *stage_buf = reinterpret_cast<uint8_t *>(lut_s + 768);
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 4 * 32 * kC1tStagePitch);
   const uint32_t fullA = smem_u32(bars), emptyA = fullA + 16, tfull = fullA + 32, tempty = fullA + 48;
@@ -134,7 +137,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
     for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
       const int b = tile / tiles_per_img, r = tile % tiles_per_img;
       const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
-      float *pt = patch + s * (18 * 10 * 3);
+      float *pt = patch + s * kC1tPatch;
       mbar_wait(emptyA + 8 * s, ph ^ 1u);     // MMAs that read this stage (and its patch) are done
       // stage the 18 x 10 x 3 mean-subtracted input patch (zero outside the image: SAME padding of the blob)
       for (int i = m; i < 18 * 10 * 3; i += 128) {
@@ -146,7 +149,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
           v = p.src_is_f32 ? reinterpret_cast<const float *>(p.src)[off]
                            : lut_s[reinterpret_cast<const uint8_t *>(p.src)[off] * 3 + c];
         }
-        pt[i] = v;
+        pt[(c * 18 + yy) * 40 + xx] = v;
       }
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this builder group
       else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -160,7 +163,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int k = chunk * 8 + j * 2 + e;       // k = (ky * 3 + kx) * 3 + c
-            v[e] = k < 27 ? pt[((th + k / 9) * 10 + tw + (k / 3) % 3) * 3 + k % 3] : 0.f;
+            v[e] = k < 27 ? pt[((k % 3) * 18 + th + k / 9) * 40 + tw + (k / 3) % 3] : 0.f;
           }
           __nv_bfloat16 h0[3], h1[3];
           split_planes(v[0], P, h0);
@@ -261,7 +264,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
 
 template <int P>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + (2 * 18 * 10 * 3 + 768) * sizeof(float) +
+  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + (2 * kC1tPatch + 768) * sizeof(float) +
                       4 * 32 * kC1tStagePitch + 64 + 16;
   CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
