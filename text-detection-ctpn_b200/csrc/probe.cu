@@ -124,6 +124,15 @@ probe_mma_rate_kernel(int n_mma, int commit_every, int lag, int alternate_acc, i
     const uint32_t idesc = umma_idesc_bf16(128, BN);
     const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
     int commits = 0, waited = 0;
+    if (fence_each == 2) {   // tight mode: 8 back-to-back MMAs per elected region, no per-MMA warp sync
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mma_bf16_ss(tmem + ((alternate_acc && (u & 4)) ? BN : 0), da + 2ull * (u & 3), db + 2ull * (u & 3), idesc, (i | u) > 7);
+        }
+        __syncwarp();
+      }
+    } else
     for (int i = 0; i < n_mma; ++i) {
       const uint32_t d = tmem + ((alternate_acc && (i & 4)) ? BN : 0);
       if (elect_one()) mma_bf16_ss(d, da + 2ull * (i & 3), db + 2ull * (i & 3), idesc, i > 7);
