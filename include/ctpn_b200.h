@@ -13,9 +13,9 @@
  *                        (called by lib/utils/gpu_nms.pyx:31)
  *   ctpn_nms_sorted      lib/utils/nms_kernel.cu:34-78 (nms_kernel) + :124-139 (host greedy scan)
  *   ctpn_proposals       lib/rpn_msr/proposal_layer_tf.py:14-157 (tf.py_func body, lib/networks/network.py:214)
- *   ctpn_conv1_1 / ctpn_conv3x3 / ctpn_maxpool2x2
+ *   ctpn_conv1_1_tc / ctpn_conv1_1 / ctpn_conv3x3 (taps=9, optional fused 2x2 max-pool)
  *                        lib/networks/network.py:160-183 (conv), :189-196 (max_pool)
- *   ctpn_bilstm_recurrent, ctpn_gemm_planes
+ *   ctpn_bilstm_recurrent, ctpn_conv3x3 (taps=1: x-projection, FC and head matmuls)
  *                        lib/networks/network.py:88-113 (Bilstm), :144-158 (lstm_fc)
  *   ctpn_net_forward     lib/networks/VGGnet_test.py:16-52 up to the two head tensors
  *                        (the demo_pb.py:73-75 boundary), fed by lib/fast_rcnn/test.py:7-31
