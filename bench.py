@@ -147,8 +147,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from ctpn_b200 import Engine, _native as N
-    from oracle import synth
+    from ctpn_b200 import Engine, _native as N, synthetic as synth     # the product arm never touches oracle/
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -94,3 +94,14 @@ def test_generate_anchors_table():
     from lib.rpn_msr.generate_anchors import generate_anchors
     np.testing.assert_array_equal(generate_anchors(), G["anchors"])
     np.testing.assert_array_equal(generate_anchors(py2=True), postproc.anchors(py2=True))
+
+
+def test_product_and_oracle_synthetic_generators_agree():
+    """bench.py's GPU arm draws its random-init weights from ctpn_b200.synthetic (the product never imports oracle/);
+    the tests and the CPU baseline use oracle.synth.  Same seeds -> same tensors."""
+    from ctpn_b200 import synthetic
+    a, b = synthetic.make_weights(0), synth.make_weights(0)
+    assert sorted(a) == sorted(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    np.testing.assert_array_equal(synthetic.make_image(3, 40, 50), synth.make_image(3, 40, 50))
