@@ -158,6 +158,10 @@ int ctpn_probe_umma_view(const void *a_bf16, const void *identity_bf16, int rows
 int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
                         int grid, void *stream);
 
+/* Hardware probe: the same back-to-back issue loop with cta_group::2 instructions (M = 256 over a 2-CTA cluster,
+ * each CTA holding its 128 A rows and bn/2 rows of B).  grid must be even; n_mma a multiple of 8. */
+int ctpn_probe_mma_rate_pair(int bn, int n_mma, int alternate_acc, int grid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

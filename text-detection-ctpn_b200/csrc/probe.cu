@@ -159,6 +159,78 @@ probe_mma_rate_kernel(int n_mma, int commit_every, int lag, int alternate_acc, i
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// ---- CTA-pair (cta_group::2) dispatch-rate probe: one instruction drives the tensor cores of both SMs of a
+// 2-CTA cluster (M = 256: 128 rows per CTA; each CTA holds its A rows and half of B's N rows). ----
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe_mma_rate_pair_kernel(int n_mma, int alternate_acc) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sa = (raw + 1023u) & ~1023u, sb = sa + 16384;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (16384 + BN * 64) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem_raw + (sa - raw))[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const bool leader = cluster_ctarank() == 0;
+  if (__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0) {
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16(256, BN);
+      const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t d = tmem + ((alternate_acc && (u & 4)) ? BN : 0);
+            const uint32_t acc = (i | u) > 7;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(d), "l"(da + 2ull * (u & 3)), "l"(db + 2ull * (u & 3)), "r"(idesc), "r"(acc)
+                : "memory");
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one())   // arrive on the barrier at this offset in BOTH CTAs once every MMA above has completed
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace ctpn
 
 extern "C" int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
@@ -171,6 +243,24 @@ extern "C" int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag,
   do {                                                                                                             \
     CTPN_CUDA(cudaFuncSetAttribute(probe_mma_rate_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     probe_mma_rate_kernel<BN><<<grid, 128, smem, st>>>(n_mma, commit_every, lag, alternate_acc, fence_each);       \
+  } while (0)
+  if (bn == 256) CTPN_LAUNCH_PROBE(256);
+  else if (bn == 128) CTPN_LAUNCH_PROBE(128);
+  else CTPN_LAUNCH_PROBE(64);
+#undef CTPN_LAUNCH_PROBE
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
+extern "C" int ctpn_probe_mma_rate_pair(int bn, int n_mma, int alternate_acc, int grid, void *stream) {
+  CTPN_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ctpn_probe_mma_rate_pair: bn must be 64/128/256");
+  CTPN_REQUIRE(n_mma > 0 && n_mma % 8 == 0 && grid > 0 && grid % 2 == 0, "ctpn_probe_mma_rate_pair: bad arguments");
+  const size_t smem = 1024 + 16384 + (size_t)bn * 64;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CTPN_LAUNCH_PROBE(BN)                                                                                      \
+  do {                                                                                                             \
+    CTPN_CUDA(cudaFuncSetAttribute(probe_mma_rate_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    probe_mma_rate_pair_kernel<BN><<<grid, 128, smem, st>>>(n_mma, alternate_acc);                                 \
   } while (0)
   if (bn == 256) CTPN_LAUNCH_PROBE(256);
   else if (bn == 128) CTPN_LAUNCH_PROBE(128);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ctpn_net_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "ctpn_net_feature_hw": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "ctpn_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _i, _p]),
+    "ctpn_probe_mma_rate_pair": (_i, [_i, _i, _i, _i, _p]),
     "ctpn_probe_umma_view": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "ctpn_net_debug_tap": (_i, [_p, C.c_char_p, _p, _z, C.POINTER(_z), _p]),
 }
