@@ -62,6 +62,23 @@ __device__ __forceinline__ void split_planes(float a, int planes, __nv_bfloat16 
   }
 }
 
+// Two floats -> P packed bf16 plane words (low half = plane of a, high half = plane of b).  One cvt.rn.bf16x2.f32 per
+// plane; the exact residual for the next plane is formed from the halves of the packed word.  Same values as
+// split_planes() on a and b separately.
+template <int P>
+__device__ __forceinline__ void split_planes2(float a, float b, uint32_t (&w)[P]) {
+#pragma unroll
+  for (int pl = 0; pl < P; ++pl) {
+    uint32_t pk;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(b), "f"(a));   // first source -> upper half
+    w[pl] = pk;
+    if (pl + 1 < P) {
+      a = __fsub_rn(a, __uint_as_float(pk << 16));
+      b = __fsub_rn(b, __uint_as_float(pk & 0xffff0000u));
+    }
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
   return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }

@@ -5,9 +5,11 @@
 //   * 4 builder warps (thread = pixel of a 16 x 8 patch) gather the 27 mean-subtracted inputs of their pixel from a
 //     small staged image patch, split them into P bf16 planes and write one K-major 128-byte row per plane in the
 //     128B-swizzled UMMA layout (only the first 64 bytes = 32 k-values are ever read),
+//   * k = 27 of the padded K = 32 carries the bias (A holds the constant 1 there), so the epilogue has no bias add,
 //   * one thread issues 2 (k-slices) x {1,3,6} (plane pairs) tcgen05.mma of shape 128 x 64 x 16 per tile against the
 //     CTA-resident weight tile (built once from the float32 HWIO weights),
-//   * 4 epilogue warps do bias + ReLU + plane split and store through the same shared-memory transpose as conv_tc.
+//   * 8 epilogue warps (two per TMEM lane quarter, one 32-channel half each) do bias + ReLU + plane split and store
+//     through the same shared-memory transpose as conv_tc -- the epilogue, not the MMAs, paces this layer.
 // Accumulators (main + cross, see conv_tc.cu) are double buffered in TMEM; the A tile is double buffered in smem.
 // Numerics: operands carry P bf16 planes like every other tensor-core layer (planes=3 is float32-equivalent).
 // Reference semantics: lib/networks/network.py:160-183 (conv1_1), lib/fast_rcnn/test.py:8-9 (mean subtraction).
@@ -16,7 +18,7 @@
 
 namespace ctpn {
 
-constexpr int kC1tThreads = 416;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-12: epilogue
+constexpr int kC1tThreads = 544;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-16: epilogue
 constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
 constexpr int kC1tStagePitch = 80;
 constexpr int kC1tPatch = 3 * 18 * 40;     // floats per staged input patch
@@ -27,6 +29,7 @@ struct Conv1TcParams {
   __nv_bfloat16 *out;
   int B, H, W, src_is_f32;
   int tiles_x, tiles_y, total_tiles;
+  int debug;   // CTPN_C1_DEBUG bits (perf experiments only): 1 skip patch staging, 2 skip tile build, 4 skip stores, 8 skip epilogue math
   long long plane_stride;
 };
 
@@ -45,7 +48,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
   float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);
   float *lut_s = patch + 2 * kC1tPatch;                                 // [256][3] mean-subtraction table
   uint8_t *stage_buf = reinterpret_cast<uint8_t *>(lut_s + 768);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 4 * 32 * kC1tStagePitch);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * 32 * kC1tStagePitch);
   const uint32_t fullA = smem_u32(bars), emptyA = fullA + 16, tfull = fullA + 32, tempty = fullA + 48;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
@@ -55,7 +58,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
       mbar_init(fullA + 8 * i, 128);     // every builder thread arrives
       mbar_init(emptyA + 8 * i, 1);      // tcgen05.commit
       mbar_init(tfull + 8 * i, 1);
-      mbar_init(tempty + 8 * i, 4);
+      mbar_init(tempty + 8 * i, 8);
     }
     fence_mbar_init();
   }
@@ -76,13 +79,12 @@ conv1_tc_kernel(const Conv1TcParams p) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int k = chunk * 8 + j * 2 + e;
-        v[e] = k < 27 ? p.w[k * 64 + co] : 0.f;
+        v[e] = k < 27 ? p.w[k * 64 + co] : (k == 27 ? p.bias[co] : 0.f);   // k = 27: bias row (A carries a 1 there)
       }
-      __nv_bfloat16 h0[3], h1[3];
-      split_planes(v[0], P, h0);
-      split_planes(v[1], P, h1);
+      uint32_t t[P];
+      split_planes2<P>(v[0], v[1], t);
 #pragma unroll
-      for (int pl = 0; pl < P; ++pl) pk[pl][j] = pack_bf16x2(h0[pl], h1[pl]);
+      for (int pl = 0; pl < P; ++pl) pk[pl][j] = t[pl];
     }
 #pragma unroll
     for (int pl = 0; pl < P; ++pl)
@@ -140,22 +142,29 @@ conv1_tc_kernel(const Conv1TcParams p) {
       float *pt = patch + s * kC1tPatch;
       mbar_wait(emptyA + 8 * s, ph ^ 1u);     // MMAs that read this stage (and its patch) are done
       // stage the 18 x 10 x 3 mean-subtracted input patch (zero outside the image: SAME padding of the blob)
-      for (int i = m; i < 18 * 10 * 3; i += 128) {
-        const int c = i % 3, xx = (i / 3) % 10, yy = i / 30;
+      for (int i = m; i < ((p.debug & 1) ? 0 : 18 * 10); i += 128) {     // thread = patch pixel: one bounds test, three adjacent loads
+        const int xx = i % 10, yy = i / 10;
         const int gx = x0 + xx - 1, gy = y0 + yy - 1;
-        float v = 0.f;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
-          const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3 + c;
-          v = p.src_is_f32 ? reinterpret_cast<const float *>(p.src)[off]
-                           : lut_s[reinterpret_cast<const uint8_t *>(p.src)[off] * 3 + c];
+          const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3;
+          if (p.src_is_f32) {
+            const float *q = reinterpret_cast<const float *>(p.src) + off;
+            v0 = q[0]; v1 = q[1]; v2 = q[2];
+          } else {
+            const uint8_t *q = reinterpret_cast<const uint8_t *>(p.src) + off;
+            v0 = lut_s[q[0] * 3 + 0]; v1 = lut_s[q[1] * 3 + 1]; v2 = lut_s[q[2] * 3 + 2];
+          }
         }
-        pt[(c * 18 + yy) * 40 + xx] = v;
+        pt[(0 * 18 + yy) * 40 + xx] = v0;
+        pt[(1 * 18 + yy) * 40 + xx] = v1;
+        pt[(2 * 18 + yy) * 40 + xx] = v2;
       }
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this builder group
       else asm volatile("bar.sync 2, 128;" ::: "memory");
       uint8_t *arow = base + s * P * kC1tTileBytes + m * 128;
 #pragma unroll
-      for (int chunk = 0; chunk < 4; ++chunk) {
+      for (int chunk = 0; chunk < ((p.debug & 2) ? 0 : 4); ++chunk) {
         uint32_t pk[3][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -163,13 +172,12 @@ conv1_tc_kernel(const Conv1TcParams p) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int k = chunk * 8 + j * 2 + e;       // k = (ky * 3 + kx) * 3 + c
-            v[e] = k < 27 ? pt[((k % 3) * 18 + th + k / 9) * 40 + tw + (k / 3) % 3] : 0.f;
+            v[e] = k < 27 ? pt[((k % 3) * 18 + th + k / 9) * 40 + tw + (k / 3) % 3] : (k == 27 ? 1.f : 0.f);
           }
-          __nv_bfloat16 h0[3], h1[3];
-          split_planes(v[0], P, h0);
-          split_planes(v[1], P, h1);
+          uint32_t t[P];
+          split_planes2<P>(v[0], v[1], t);
 #pragma unroll
-          for (int pl = 0; pl < P; ++pl) pk[pl][j] = pack_bf16x2(h0[pl], h1[pl]);
+          for (int pl = 0; pl < P; ++pl) pk[pl][j] = t[pl];
         }
 #pragma unroll
         for (int pl = 0; pl < P; ++pl)
@@ -180,7 +188,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
       ph ^= 1u;
     }
   } else {
-    // ===== epilogue warps 9..12 (TMEM lane quarter = warp & 3) =====
+    // ===== epilogue warps 9..16 (TMEM lane quarter = warp & 3; warps 9-12 take channels 0-31, 13-16 channels 32-63) =====
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane, th = m >> 3, tw = m & 7;
     uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + (warp - 9) * 32 * kC1tStagePitch);
@@ -202,8 +210,8 @@ conv1_tc_kernel(const Conv1TcParams p) {
       mbar_wait(tfull + 8 * a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
-#pragma unroll 1
-      for (int chunk = 0; chunk < 2; ++chunk) {
+      if (!(p.debug & 8)) {
+        const int chunk = (warp - 9) >> 2;
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
         tmem_ld_wait();
@@ -218,33 +226,27 @@ conv1_tc_kernel(const Conv1TcParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
         }
+        // the bias came in through the tensor core (k = 27 row of the weight tile x the builders' constant 1)
+        uint32_t w[P][16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bq = __ldg(reinterpret_cast<const float4 *>(p.bias + chunk * 32) + q);
-          v[4 * q + 0] = fmaxf(v[4 * q + 0] + bq.x, 0.f);
-          v[4 * q + 1] = fmaxf(v[4 * q + 1] + bq.y, 0.f);
-          v[4 * q + 2] = fmaxf(v[4 * q + 2] + bq.z, 0.f);
-          v[4 * q + 3] = fmaxf(v[4 * q + 3] + bq.w, 0.f);
+        for (int i = 0; i < 16; ++i) {
+          uint32_t t[P];
+          split_planes2<P>(fmaxf(v[2 * i], 0.f), fmaxf(v[2 * i + 1], 0.f), t);
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) w[pl][i] = t[pl];
         }
-        for (int pl = 0; pl < P; ++pl) {
-          uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-            w[i] = pack_bf16x2(h0, h1);
-            v[2 * i] = __fsub_rn(v[2 * i], __bfloat162float(h0));
-            v[2 * i + 1] = __fsub_rn(v[2 * i + 1], __bfloat162float(h1));
-          }
+        for (int pl = 0; pl < P; ++pl) {
           __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) stage_w[lane * (kC1tStagePitch / 16) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) stage_w[lane * (kC1tStagePitch / 16) + q] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
           __syncwarp();
           __nv_bfloat16 *obase = p.out + (long long)pl * p.plane_stride + chunk * 32 + (lane & 3) * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int pp = it * 8 + (lane >> 2);
             const uint4 val = stage_w[pp * (kC1tStagePitch / 16) + (lane & 3)];
-            if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
+            if (((okmask >> pp) & 1u) && !(p.debug & 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
           }
         }
       }
@@ -265,7 +267,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
 template <int P>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + (2 * kC1tPatch + 768) * sizeof(float) +
-                      4 * 32 * kC1tStagePitch + 64 + 16;
+                      8 * 32 * kC1tStagePitch + 64 + 16;
   CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   CTPN_CUDA(cudaGetDevice(&dev));
@@ -295,6 +297,10 @@ extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut
   CTPN_REQUIRE(total < (1ll << 31), "ctpn_conv1_1_tc: too many tiles");
   p.total_tiles = (int)total;
   p.plane_stride = (long long)B * H * W * 64;
+  {
+    const char *e = getenv("CTPN_C1_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 1) return launch_conv1_tc<1>(p, st);
   if (planes == 2) return launch_conv1_tc<2>(p, st);

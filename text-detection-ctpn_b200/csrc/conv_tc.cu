@@ -297,18 +297,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (!out_f32) {
-          for (int pl = 0; pl < P; ++pl) {
-            uint32_t w[16];
+          uint32_t w[P][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-              w[i] = pack_bf16x2(h0, h1);
-              v[2 * i] = __fsub_rn(v[2 * i], __bfloat162float(h0));       // exact residual for the next plane
-              v[2 * i + 1] = __fsub_rn(v[2 * i + 1], __bfloat162float(h1));
-            }
+          for (int i = 0; i < 16; ++i) {
+            uint32_t t[P];
+            split_planes2<P>(v[2 * i], v[2 * i + 1], t);
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl) w[pl][i] = t[pl];
+          }
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) {
             __syncwarp();     // previous readers of the staging block are done
 #pragma unroll
-            for (int q = 0; q < 4; ++q) stage_w[lane * (kStagePitch / 16) + q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) stage_w[lane * (kStagePitch / 16) + q] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
             __syncwarp();
             if (c0 < p.Cout && !(p.debug & 8)) {
               __nv_bfloat16 *obase = reinterpret_cast<__nv_bfloat16 *>(p.out) + (long long)pl * p.out_plane_stride + c0 + (lane & 3) * 8;
