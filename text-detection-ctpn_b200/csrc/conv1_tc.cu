@@ -10,7 +10,9 @@
 //     CTA-resident weight tile (built once from the float32 HWIO weights),
 //   * 8 epilogue warps (two per TMEM lane quarter, one 32-channel half each) do bias + ReLU + plane split and store
 //     through the same shared-memory transpose as conv_tc -- the epilogue, not the MMAs, paces this layer.
-// Accumulators (main + cross, see conv_tc.cu) are double buffered in TMEM; the A tile is double buffered in smem.
+// Accumulators (main + cross, see conv_tc.cu) are double buffered in TMEM.  Each builder group owns kSPG A stages
+// (two for P <= 2), so it starts its next tile while the MMAs of the previous one are still in flight -- with one
+// stage per group the builder sat idle for the arrive -> MMA -> commit round trip (~1000 cycles) on every tile.
 // Numerics: operands carry P bf16 planes like every other tensor-core layer (planes=3 is float32-equivalent).
 // Reference semantics: lib/networks/network.py:160-183 (conv1_1), lib/fast_rcnn/test.py:8-9 (mean subtraction).
 #include "common.cuh"
@@ -20,7 +22,7 @@ namespace ctpn {
 
 constexpr int kC1tThreads = 544;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-16: epilogue
 constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
-constexpr int kC1tStagePitch = 80;
+constexpr int kC1tStagePitch = 64;          // epilogue staging rows: 64 B, 16-byte chunks XOR-swizzled by (row >> 1) & 3
 constexpr int kC1tPatch = 3 * 18 * 40;     // floats per staged input patch
 
 struct Conv1TcParams {
@@ -39,24 +41,28 @@ conv1_tc_kernel(const Conv1TcParams p) {
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t a0 = (raw + 1023u) & ~1023u;                 // A tiles: [2 stages][P planes][16 KB]
-  const uint32_t b0 = a0 + 2u * P * kC1tTileBytes;            // weights: [P planes][64 rows x 128 B]
+  constexpr int kSPG = P <= 2 ? 2 : 1;                        // A stages per builder group
+  constexpr int kStages = 2 * kSPG;
+  const uint32_t a0 = (raw + 1023u) & ~1023u;                 // A tiles: [kStages][P planes][16 KB]
+  const uint32_t b0 = a0 + (uint32_t)kStages * P * kC1tTileBytes;   // weights: [P planes][64 rows x 128 B]
   uint8_t *base = smem_raw + (a0 - raw);
-  uint8_t *bsm = base + 2 * P * kC1tTileBytes;
-  // input patch per stage: [3 channels][18 rows][40]: a row pitch of 40 floats makes the builders' gather
+  uint8_t *bsm = base + kStages * P * kC1tTileBytes;
+  // input patches (two per builder group): [3 channels][18 rows][40]: a row pitch of 40 floats makes the builders' gather
   // (lanes = 4 tile rows x 8 tile columns) hit 32 distinct banks
   float *patch = reinterpret_cast<float *>(bsm + P * 64 * 128);
-  float *lut_s = patch + 2 * kC1tPatch;                                 // [256][3] mean-subtraction table
+  float *lut_s = patch + 4 * kC1tPatch;                                 // [256][3] mean-subtraction table
   uint8_t *stage_buf = reinterpret_cast<uint8_t *>(lut_s + 768);
   uint64_t *bars = reinterpret_cast<uint64_t *>(stage_buf + 8 * 32 * kC1tStagePitch);
-  const uint32_t fullA = smem_u32(bars), emptyA = fullA + 16, tfull = fullA + 32, tempty = fullA + 48;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  const uint32_t fullA = smem_u32(bars), emptyA = fullA + 32, tfull = fullA + 64, tempty = fullA + 80;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(fullA + 8 * i, 128);     // every builder thread arrives
       mbar_init(emptyA + 8 * i, 1);      // tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(tfull + 8 * i, 1);
       mbar_init(tempty + 8 * i, 8);
     }
@@ -101,9 +107,12 @@ conv1_tc_kernel(const Conv1TcParams p) {
     // ===== MMA issuer =====
     constexpr uint32_t kIdesc = umma_idesc_bf16(128, 64);
     constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    int s = 0, a = 0;
-    uint32_t ph = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int a = 0, n = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++n) {
+      // tile n of this CTA was built by group n & 1 as its (n >> 1)-th tile
+      const int s = (n & 1) * kSPG + (n >> 1) % kSPG;
+      const uint32_t ph = (uint32_t)((n >> 1) / kSPG) & 1u;
       mbar_wait(tempty + 8 * a, aph ^ 1u);
       mbar_wait(fullA + 8 * s, ph);
       tc_fence_after();
@@ -126,7 +135,6 @@ conv1_tc_kernel(const Conv1TcParams p) {
         mma_commit(tfull + 8 * a);
       }
       __syncwarp();
-      if (++s == 2) { s = 0; ph ^= 1u; }
       if (++a == 2) { a = 0; aph ^= 1u; }
     }
   } else if (warp <= 8) {
@@ -134,32 +142,64 @@ conv1_tc_kernel(const Conv1TcParams p) {
     // so two tiles are in flight and the global-load latency of the patch staging is hidden.  thread = pixel m =====
     const int grp = (warp - 1) >> 2;
     const int m = ((warp - 1) & 3) * 32 + lane, th = m >> 3, tw = m & 7;
-    const int s = grp;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x) {
-      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-      const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
-      float *pt = patch + s * kC1tPatch;
-      mbar_wait(emptyA + 8 * s, ph ^ 1u);     // MMAs that read this stage (and its patch) are done
-      // stage the 18 x 10 x 3 mean-subtracted input patch (zero outside the image: SAME padding of the blob)
-      for (int i = m; i < ((p.debug & 1) ? 0 : 18 * 10); i += 128) {     // thread = patch pixel: one bounds test, three adjacent loads
+    // The raw inputs of the NEXT tile's patch pixels (this thread stages patch pixels m and m + 128 of 180) are
+    // fetched into registers while the current tile is being built, so the global-load latency is off the
+    // per-tile critical path of the group.
+    const unsigned tpi = (unsigned)tiles_per_img, tx = (unsigned)p.tiles_x;
+    uint32_t raw[2][3];
+    unsigned valid = 0;
+    auto fetch = [&](int tile) {
+      valid = 0;
+      if (tile >= p.total_tiles) return;
+      const unsigned b = (unsigned)tile / tpi, r = (unsigned)tile % tpi;
+      const int y0 = (int)(r / tx) * 16, x0 = (int)(r % tx) * 8;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = m + u * 128;
         const int xx = i % 10, yy = i / 10;
         const int gx = x0 + xx - 1, gy = y0 + yy - 1;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
+        if (i < 180 && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && !(p.debug & 1)) {
           const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3;
           if (p.src_is_f32) {
             const float *q = reinterpret_cast<const float *>(p.src) + off;
-            v0 = q[0]; v1 = q[1]; v2 = q[2];
+            raw[u][0] = __float_as_uint(q[0]); raw[u][1] = __float_as_uint(q[1]); raw[u][2] = __float_as_uint(q[2]);
           } else {
             const uint8_t *q = reinterpret_cast<const uint8_t *>(p.src) + off;
-            v0 = lut_s[q[0] * 3 + 0]; v1 = lut_s[q[1] * 3 + 1]; v2 = lut_s[q[2] * 3 + 2];
+            raw[u][0] = q[0]; raw[u][1] = q[1]; raw[u][2] = q[2];
           }
+          valid |= 1u << u;
         }
-        pt[(0 * 18 + yy) * 40 + xx] = v0;
-        pt[(1 * 18 + yy) * 40 + xx] = v1;
-        pt[(2 * 18 + yy) * 40 + xx] = v2;
       }
+    };
+    fetch(blockIdx.x + grp * gridDim.x);
+    int n = 0;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, ++n) {
+      const int s = grp * kSPG + n % kSPG;
+      const uint32_t ph = (uint32_t)(n / kSPG) & 1u;
+      // two patches per group: a fast warp may stage tile n + 1 while a slow one still gathers from tile n's patch;
+      // it cannot get to tile n + 2 before the group barrier of tile n + 1, which the slow warp reaches after tile n
+      float *pt = patch + (grp * 2 + (n & 1)) * kC1tPatch;
+      // stage the 18 x 10 x 3 mean-subtracted input patch (zero outside the image: SAME padding of the blob)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = m + u * 128;
+        if (i < 180) {
+          const int xx = i % 10, yy = i / 10;
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+          if ((valid >> u) & 1u) {
+            if (p.src_is_f32) {
+              v0 = __uint_as_float(raw[u][0]); v1 = __uint_as_float(raw[u][1]); v2 = __uint_as_float(raw[u][2]);
+            } else {
+              v0 = lut_s[raw[u][0] * 3 + 0]; v1 = lut_s[raw[u][1] * 3 + 1]; v2 = lut_s[raw[u][2] * 3 + 2];
+            }
+          }
+          pt[(0 * 18 + yy) * 40 + xx] = v0;
+          pt[(1 * 18 + yy) * 40 + xx] = v1;
+          pt[(2 * 18 + yy) * 40 + xx] = v2;
+        }
+      }
+      fetch(tile + 2 * gridDim.x);            // next tile of this group: loads stay in flight during the build
+      mbar_wait(emptyA + 8 * s, ph ^ 1u);     // MMAs that read this A stage are done
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the four warps of this builder group
       else asm volatile("bar.sync 2, 128;" ::: "memory");
       uint8_t *arow = base + s * P * kC1tTileBytes + m * 128;
@@ -185,7 +225,6 @@ conv1_tc_kernel(const Conv1TcParams p) {
       }
       fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(fullA + 8 * s);
-      ph ^= 1u;
     }
   } else {
     // ===== epilogue warps 9..16 (TMEM lane quarter = warp & 3; warps 9-12 take channels 0-31, 13-16 channels 32-63) =====
@@ -195,8 +234,8 @@ conv1_tc_kernel(const Conv1TcParams p) {
     int a = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_img, r = tile % tiles_per_img;
-      const int y = (r / p.tiles_x) * 16 + th, x = (r % p.tiles_x) * 8 + tw;
+      const unsigned b = (unsigned)tile / (unsigned)tiles_per_img, r = (unsigned)tile % (unsigned)tiles_per_img;
+      const int y = (int)(r / (unsigned)p.tiles_x) * 16 + th, x = (int)(r % (unsigned)p.tiles_x) * 8 + tw;
       const bool ok = y < p.H && x < p.W;
       const long long pix = ((long long)b * p.H + y) * p.W + x;
       const unsigned okmask = __ballot_sync(0xffffffffu, ok);
@@ -239,13 +278,13 @@ conv1_tc_kernel(const Conv1TcParams p) {
         for (int pl = 0; pl < P; ++pl) {
           __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) stage_w[lane * (kC1tStagePitch / 16) + q] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
+          for (int q = 0; q < 4; ++q) stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
           __syncwarp();
           __nv_bfloat16 *obase = p.out + (long long)pl * p.plane_stride + chunk * 32 + (lane & 3) * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int pp = it * 8 + (lane >> 2);
-            const uint4 val = stage_w[pp * (kC1tStagePitch / 16) + (lane & 3)];
+            const uint4 val = stage_w[pp * 4 + ((lane & 3) ^ ((pp >> 1) & 3))];
             if (((okmask >> pp) & 1u) && !(p.debug & 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
           }
         }
@@ -266,8 +305,8 @@ conv1_tc_kernel(const Conv1TcParams p) {
 
 template <int P>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)2 * P * kC1tTileBytes + (size_t)P * 64 * 128 + (2 * kC1tPatch + 768) * sizeof(float) +
-                      8 * 32 * kC1tStagePitch + 64 + 16;
+  const size_t smem = 1024 + (size_t)(P <= 2 ? 4 : 2) * P * kC1tTileBytes + (size_t)P * 64 * 128 + (4 * kC1tPatch + 768) * sizeof(float) +
+                      8 * 32 * kC1tStagePitch + 96 + 16;
   CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 0;
   CTPN_CUDA(cudaGetDevice(&dev));

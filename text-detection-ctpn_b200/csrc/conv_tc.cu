@@ -51,7 +51,8 @@ struct ConvTcParams {
 constexpr int kTcThreads = 352;   // warps: 0 B-producer, 1 MMA, 2-5 epilogue set 0, 6 A-producer, 7-10 epilogue set 1
 constexpr int kMaxStages = 8;
 constexpr int kCtrlBytes = 8 * (4 * kMaxStages + 4) + 16;
-constexpr int kStagePitch = 80;                    // bytes per pixel row of the epilogue staging buffer (64 B + 16 B pad)
+constexpr int kStagePitch = 64;                    // bytes per pixel row of the epilogue staging buffer; 16-B chunks are
+                                                   // XOR-swizzled by (row >> 1) & 3: conflict-free writes AND reads
 constexpr int kStageBytes = 8 * 32 * kStagePitch;  // one 32-pixel x 32-channel bf16 block per epilogue warp
 
 __device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_t group_stride_bytes) {
@@ -309,14 +310,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int pl = 0; pl < P; ++pl) {
             __syncwarp();     // previous readers of the staging block are done
 #pragma unroll
-            for (int q = 0; q < 4; ++q) stage_w[lane * (kStagePitch / 16) + q] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
+            for (int q = 0; q < 4; ++q) stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
             __syncwarp();
             if (c0 < p.Cout && !(p.debug & 8)) {
               __nv_bfloat16 *obase = reinterpret_cast<__nv_bfloat16 *>(p.out) + (long long)pl * p.out_plane_stride + c0 + (lane & 3) * 8;
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int pp = it * 8 + (lane >> 2);
-                const uint4 val = stage_w[pp * (kStagePitch / 16) + (lane & 3)];
+                const uint4 val = stage_w[pp * 4 + ((lane & 3) ^ ((pp >> 1) & 3))];
                 if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout) = val;
               }
             }
