@@ -7,7 +7,8 @@
 // units: CTA r keeps the 4 x 64 gate columns of units [64r, 64r+64) (128 KiB) resident in shared
 // memory for the whole sequence and the two CTAs exchange their halves of h_t through
 // distributed shared memory once per step.  Each cluster advances RG independent rows of one
-// direction, so Wh is read from shared memory once per RG rows.  All arithmetic is float32.
+// direction, so Wh is read from shared memory once per RG rows.  All arithmetic is float32; the mat-vec uses the
+// packed fma.rn.f32x2 of sm_100 (two k per instruction: even-k and odd-k partial sums, added at the end).
 //
 // TF 1.3 LSTMCell: gates (i, j, f, o) = [x, h] . kernel + bias;
 //   c = sigmoid(f + 1) * c + sigmoid(i) * tanh(j);  h = sigmoid(o) * tanh(c).
@@ -45,9 +46,14 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
   const int gcol0 = (lc0 >> 6) * kHid + rank * kHalf + (lc0 & 63);   // column in the 512-wide gate vector
   const int ul = t & 63;
   const float *wh = dir ? wh_bw : wh_fw;
+  // Shared-memory layout of the weights for packed (f32x2) FMAs: [column pair half][k pair][column group][4] with
+  // the 4 floats = (col a: k even, k odd; col b: k even, k odd), so one LDS.128 hands a thread two (k, k+1) weight
+  // pairs and consecutive lanes read consecutive 16-byte chunks (conflict-free).
   for (int i = t; i < kHid * kLocalCols; i += 256) {
     const int k = i >> 8, lc = i & 255;
-    Ws[i] = wh[k * kGates + (lc >> 6) * kHid + rank * kHalf + (lc & 63)];
+    const int cgi = lc >> 2, cc = lc & 3;
+    Ws[(((cc >> 1) * (kHid / 2) + (k >> 1)) * 64 + cgi) * 4 + (cc & 1) * 2 + (k & 1)] =
+        wh[k * kGates + (lc >> 6) * kHid + rank * kHalf + (lc & 63)];
   }
   for (int i = t; i < 2 * RG * kHid; i += 256) hbuf[i] = 0.f;
   float *peer_h = cluster.map_shared_rank(hbuf, rank ^ 1);
@@ -57,38 +63,59 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
   cluster.sync();
 
   const long long plane_stride = (long long)R * W * 2 * kHid;
+  float4 xnext[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const int row = row0 + rg * RT + r;
+    xnext[r] = row < R ? __ldg(reinterpret_cast<const float4 *>(xproj + ((long long)row * W + (dir ? W - 1 : 0)) * (2 * kGates) + dir * kGates + gcol0))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int step = 0; step < W; ++step) {
     const int tpos = dir ? W - 1 - step : step;
     const float *hc = hbuf + (step & 1) * RG * kHid;
     float *hn = hbuf + ((step + 1) & 1) * RG * kHid;
     float *hn_peer = peer_h + ((step + 1) & 1) * RG * kHid;
-    float4 acc[RT];
+    // acc[r][c] = (sum over even k, sum over odd k) for local column lc0 + c: one FFMA2 (sm_100 fma.rn.f32x2)
+    // advances two k at once with the natural register pairs (h[k], h[k+1]) x (w[k][c], w[k+1][c]).
+    float2 acc[RT][4];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      const int row = row0 + rg * RT + r;
-      acc[r] = row < R ? __ldg(reinterpret_cast<const float4 *>(xproj + ((long long)row * W + tpos) * (2 * kGates) + dir * kGates + gcol0))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 x = xnext[r];
+      acc[r][0] = make_float2(x.x, 0.f); acc[r][1] = make_float2(x.y, 0.f);
+      acc[r][2] = make_float2(x.z, 0.f); acc[r][3] = make_float2(x.w, 0.f);
     }
+    if (step + 1 < W) {   // x-projection of the next step: in flight during this step's mat-vec
+      const int tn = dir ? W - 2 - step : step + 1;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int row = row0 + rg * RT + r;
+        if (row < R) xnext[r] = __ldg(reinterpret_cast<const float4 *>(xproj + ((long long)row * W + tn) * (2 * kGates) + dir * kGates + gcol0));
+      }
+    }
+    const float4 *w_lo = reinterpret_cast<const float4 *>(Ws) + cg;                       // columns lc0, lc0 + 1
+    const float4 *w_hi = reinterpret_cast<const float4 *>(Ws) + (kHid / 2) * 64 + cg;     // columns lc0 + 2, lc0 + 3
 #pragma unroll 2
     for (int k = 0; k < kHid; k += 4) {
-      float4 w[4];
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4 *>(Ws + (k + kk) * kLocalCols + lc0);
+      const float4 wa0 = w_lo[(k >> 1) * 64], wa1 = w_lo[((k >> 1) + 1) * 64];
+      const float4 wb0 = w_hi[(k >> 1) * 64], wb1 = w_hi[((k >> 1) + 1) * 64];
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
         const float4 h4 = *reinterpret_cast<const float4 *>(hc + (rg * RT + r) * kHid + k);
-        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          acc[r].x = fmaf(hv[kk], w[kk].x, acc[r].x);
-          acc[r].y = fmaf(hv[kk], w[kk].y, acc[r].y);
-          acc[r].z = fmaf(hv[kk], w[kk].z, acc[r].z);
-          acc[r].w = fmaf(hv[kk], w[kk].w, acc[r].w);
-        }
+        const float2 h01 = make_float2(h4.x, h4.y), h23 = make_float2(h4.z, h4.w);
+        acc[r][0] = __ffma2_rn(h01, make_float2(wa0.x, wa0.y), acc[r][0]);
+        acc[r][1] = __ffma2_rn(h01, make_float2(wa0.z, wa0.w), acc[r][1]);
+        acc[r][2] = __ffma2_rn(h01, make_float2(wb0.x, wb0.y), acc[r][2]);
+        acc[r][3] = __ffma2_rn(h01, make_float2(wb0.z, wb0.w), acc[r][3]);
+        acc[r][0] = __ffma2_rn(h23, make_float2(wa1.x, wa1.y), acc[r][0]);
+        acc[r][1] = __ffma2_rn(h23, make_float2(wa1.z, wa1.w), acc[r][1]);
+        acc[r][2] = __ffma2_rn(h23, make_float2(wb1.x, wb1.y), acc[r][2]);
+        acc[r][3] = __ffma2_rn(h23, make_float2(wb1.z, wb1.w), acc[r][3]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < RT; ++r) *reinterpret_cast<float4 *>(gates + (rg * RT + r) * kLocalCols + lc0) = acc[r];
+    for (int r = 0; r < RT; ++r)
+      *reinterpret_cast<float4 *>(gates + (rg * RT + r) * kLocalCols + lc0) =
+          make_float4(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y, acc[r][2].x + acc[r][2].y, acc[r][3].x + acc[r][3].y);
     __syncthreads();
     // cell update: thread -> unit ul, rows (t>>6) + 4q
 #pragma unroll

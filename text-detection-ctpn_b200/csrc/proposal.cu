@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kSortThreads)
 proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restrict__ valid,
                      const float4 *__restrict__ boxes, int NA, int max_n, uint2 *__restrict__ buf_a,
                      uint2 *__restrict__ buf_b, float4 *__restrict__ sorted_boxes,
-                     int *__restrict__ sorted_idx, int *__restrict__ counts) {
+                     int *__restrict__ sorted_idx, int *__restrict__ counts, int W_cols, int *__restrict__ col_start) {
   extern __shared__ int sort_smem[];
   int *hist = sort_smem;                   // [256]
   int *base = hist + 256;                  // [256]
@@ -116,7 +116,11 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
   uint2 *bufs[2] = {buf_a + (size_t)img * NA, buf_b + (size_t)img * NA};
   for (int k = tid; k < kSortWarps * 256; k += kSortThreads) wc[k] = 0;
   int n_in = NA;
-  for (int pass = 0; pass < 4; ++pass) {
+  // passes 0-3: the 32-bit score key.  Optional pass 4 (W_cols > 0): the top max_n entries, stably re-bucketed by
+  // feature-map column (payload = position in the score order) for the column-wise NMS -- each column's candidates
+  // end up contiguous and still in score order, so the NMS CTAs do not have to scan the whole list.
+  const int npass = W_cols > 0 ? 5 : 4;
+  for (int pass = 0; pass < npass; ++pass) {
     const int shift = 8 * pass;
     const uint2 *src = bufs[(pass + 1) & 1];   // pass 0 reads keys/valid instead
     uint2 *dst = bufs[pass & 1];
@@ -126,7 +130,8 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
       bool has;
       uint32_t key;
       if (pass == 0) { has = v0[i] != 0; key = k0[i]; } else { has = true; key = src[i].x; }
-      if (has) atomicAdd(&hist[(key >> shift) & 255], 1);
+      if (pass == 4) atomicAdd(&hist[(src[i].y / 10u) % (uint32_t)W_cols], 1);
+      else if (has) atomicAdd(&hist[(key >> shift) & 255], 1);
     }
     __syncthreads();
     if (warp == 0) {   // exclusive scan of 256 bins: 8 per lane
@@ -144,6 +149,8 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
       for (int k = 0; k < 8; ++k) { base[lane * 8 + k] = run; run += loc[k]; }
     }
     __syncthreads();
+    if (pass == 4 && tid <= W_cols) col_start[img * 257 + tid] = tid < 256 ? base[tid] : n_in;
+    if (pass == 4) __syncthreads();
     for (int start = 0; start < n_in; start += kSortThreads) {
       const int i = start + tid;
       bool has = i < n_in;
@@ -152,7 +159,7 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
         if (pass == 0) { has = v0[i] != 0; key = k0[i]; idx = (uint32_t)i; }
         else { uint2 p = src[i]; key = p.x; idx = p.y; }
       }
-      const uint32_t d = has ? ((key >> shift) & 255u) : 0x1FFu;
+      const uint32_t d = !has ? 0x1FFu : pass == 4 ? (idx / 10u) % (uint32_t)W_cols : ((key >> shift) & 255u);
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const int rank = __popc(peers & ((1u << lane) - 1u));
       if (has && rank == 0) wc[warp * 256 + d] = __popc(peers);
@@ -169,7 +176,7 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
         base[tid] = run;
       }
       __syncthreads();
-      if (has) dst[wo[warp * 256 + d] + rank] = make_uint2(key, idx);
+      if (has) dst[wo[warp * 256 + d] + rank] = make_uint2(pass == 4 ? (uint32_t)i : key, idx);
     }
     __syncthreads();
     if (pass == 0) {   // number of valid candidates = total of the first histogram
@@ -177,6 +184,7 @@ proposal_sort_kernel(const uint32_t *__restrict__ keys, const uint8_t *__restric
       __syncthreads();
       n_in = s_total;
     }
+    if (pass == 3) n_in = min(n_in, max_n);   // only the top max_n take part in the column pass
   }
   // after 4 passes the result sits in bufs[1]; keep the top max_n and gather their boxes
   const uint2 *res = bufs[1];
@@ -224,7 +232,8 @@ constexpr int kColThreads = 256;
 __global__ void __launch_bounds__(kColThreads)
 proposal_column_nms_kernel(const float4 *__restrict__ sorted_boxes, const int *__restrict__ sorted_idx,
                            const int *__restrict__ counts, const int *__restrict__ unstructured, int max_n, int H,
-                           int W, float thresh, uint8_t *__restrict__ kept_flags) {
+                           int W, float thresh, uint8_t *__restrict__ kept_flags, const uint2 *__restrict__ colbuf,
+                           const int *__restrict__ col_start, int NA) {
   const int col = blockIdx.x, img = blockIdx.y;
   if (unstructured[img]) return;
   const int cap = H * 10, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -239,6 +248,19 @@ proposal_column_nms_kernel(const float4 *__restrict__ sorted_boxes, const int *_
   const float4 *sb = sorted_boxes + (size_t)img * max_n;
   const int *si = sorted_idx + (size_t)img * max_n;
   int total = 0;
+  if (col_start) {   // the sort kernel already bucketed the score-ordered list by column
+    const int seg0 = col_start[img * 257 + col];
+    total = col_start[img * 257 + col + 1] - seg0;
+    const uint2 *cb = colbuf + (size_t)img * NA + seg0;
+    for (int k = tid; k < min(total, cap); k += kColThreads) {
+      const int r = (int)cb[k].x;
+      pos[k] = r;
+      const float4 b = sb[r];
+      box[k] = b;
+      area[k] = box_area(b);
+    }
+    __syncthreads();
+  } else
   for (int base = 0; base < n; base += kColThreads) {
     const int r = base + tid;
     const bool pred = r < n && ((si[r] / 10) % W == col);
@@ -317,7 +339,7 @@ static size_t column_smem_bytes(int H) {
 
 struct ProposalWs {
   size_t boxes, scores, keys, valid, buf_a, buf_b, sorted_boxes, sorted_idx, counts, keep, num, mask, total;
-  size_t unstructured, kept_flags;
+  size_t unstructured, kept_flags, col_start;
   size_t mask_bytes;
 };
 
@@ -338,6 +360,7 @@ static ProposalWs proposal_layout(int batch, int NA, int max_n, int post) {
   w.num = take((size_t)batch * sizeof(int));
   w.unstructured = take((size_t)batch * sizeof(int));
   w.kept_flags = take((size_t)batch * max_n);
+  w.col_start = take((size_t)batch * 257 * sizeof(int));
   w.mask_bytes = ctpn_nms_workspace_bytes(batch, max_n);
   w.mask = take(w.mask_bytes);
   w.total = o;
@@ -398,15 +421,20 @@ extern "C" int ctpn_proposals(const float *cls, int cls_is_logit, const float *b
                                              try_columns ? unstructured : nullptr);
   CTPN_LAUNCH_CHECK();
   CTPN_CUDA(cudaFuncSetAttribute(proposal_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+  // W <= 256: the sort kernel also buckets the survivors by column (one more 8-bit pass)
+  const bool bucket = try_columns && W <= 256 && !getenv("CTPN_COLUMN_GATHER");
+  int *col_start = (int *)(ws + w.col_start);
   proposal_sort_kernel<<<batch, kSortThreads, kSortSmem, st>>>(keys, valid, boxes, NA, max_n, (uint2 *)(ws + w.buf_a),
-                                                       (uint2 *)(ws + w.buf_b), sorted_boxes, sorted_idx, counts);
+                                                       (uint2 *)(ws + w.buf_b), sorted_boxes, sorted_idx, counts,
+                                                       bucket ? W : 0, col_start);
   CTPN_LAUNCH_CHECK();
   if (try_columns) {
     uint8_t *kept_flags = (uint8_t *)(ws + w.kept_flags);
     if (col_smem > 48 * 1024)
       CTPN_CUDA(cudaFuncSetAttribute(proposal_column_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
     proposal_column_nms_kernel<<<dim3(W, batch), kColThreads, col_smem, st>>>(sorted_boxes, sorted_idx, counts, unstructured,
-                                                                           max_n, H, W, nms_thresh, kept_flags);
+                                                                           max_n, H, W, nms_thresh, kept_flags,
+                                                                           (const uint2 *)(ws + w.buf_a), bucket ? col_start : nullptr, NA);
     CTPN_LAUNCH_CHECK();
     proposal_compact_kernel<<<batch, 1024, 0, st>>>(kept_flags, counts, unstructured, max_n, post, keep, num);
     CTPN_LAUNCH_CHECK();
