@@ -14,9 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 RELU, POOL, F32 = 1, 2, 4
 
 
-def run_check(*args, timeout=300):
+def run_check(*args, timeout=300, env=None):
     cmd = [sys.executable, os.path.join(HERE, "gpu_checks.py")] + [str(a) for a in args]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
     assert lines, "no result line.\nstdout:\n%s\nstderr:\n%s" % (p.stdout[-2000:], p.stderr[-3000:])
     res = json.loads(lines[-1])
@@ -50,6 +50,12 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
 def test_conv_tcgen05(case):
     run_check(*conv_args(*case))
+
+
+@pytest.mark.parametrize("case", [TC_CASES[4], TC_CASES[5], TC_CASES[7]], ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
+def test_conv_tcgen05_single_cta_variant(case):
+    """3x3 layers default to 2-CTA clusters with multicast weight tiles; CTPN_TC_MCAST=0 is the one-CTA-per-tile variant."""
+    run_check(*conv_args(*case), env={"CTPN_TC_MCAST": "0"})
 
 
 SIMT_CASES = [

@@ -162,15 +162,6 @@ probe_mma_rate_kernel(int n_mma, int commit_every, int lag, int alternate_acc, i
 
 // ---- CTA-pair (cta_group::2) dispatch-rate probe: one instruction drives the tensor cores of both SMs of a
 // 2-CTA cluster (M = 256: 128 rows per CTA; each CTA holds its A rows and half of B's N rows). ----
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 probe_mma_rate_pair_kernel(int n_mma, int alternate_acc) {
@@ -195,7 +186,7 @@ probe_mma_rate_pair_kernel(int n_mma, int alternate_acc) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const bool leader = cluster_ctarank() == 0;
+  const bool leader = ptx::cluster_ctarank() == 0;
   if (__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0) {
     if (leader) {
       const uint32_t idesc = umma_idesc_bf16(256, BN);
