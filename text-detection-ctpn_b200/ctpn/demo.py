@@ -1,6 +1,6 @@
 """Command-line demo with the call structure of the reference's ctpn/demo.py:
 
-    python ctpn/demo.py [--weights W.npz] [--planes 2] [--images 'data/demo/*']
+    python ctpn/demo.py [--weights CKPT_DIR|model.ckpt|ctpn.pb|W.npz] [--planes 2] [--images 'data/demo/*']
 
 ctpn(sess, net, image_name) keeps the reference signature (demo.py:55-68): read image, resize
 (short side 600, long side <= 1200), test_ctpn, TextDetector, write data/results/res_<stem>.txt
@@ -74,7 +74,9 @@ def ctpn(sess, net, image_name):
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("--weights", default=None, help=".npz of TF variables (default: synthetic seed-0 weights)")
+    ap.add_argument("--weights", default=None,
+                    help="TF checkpoint prefix / directory, frozen .pb, VGG .npy or .npz (default: cfg.TEST.checkpoints_path, "
+                         "like demo.py:88-90)")
     ap.add_argument("--planes", type=int, default=2)
     ap.add_argument("--images", default=os.path.join(cfg.DATA_DIR, 'demo', '*'))
     ap.add_argument("--cfg", default=os.path.join(_PKG, 'ctpn', 'text.yml'))
@@ -87,10 +89,13 @@ def main(argv=None):
     sess = Session(planes=args.planes, device=cfg.GPU_ID)
     net = get_network("VGGnet_test")
     print('Loading network VGGnet_test... ', end=' ')
-    if args.weights is None:
-        raise SystemExit("--weights is required (an .npz with the TF variable names of SURVEY.md App. A.2)")
-    sess.restore(args.weights)
-    print('done')
+    weights = args.weights if args.weights is not None else cfg.TEST.checkpoints_path
+    try:        # demo.py:87-93: get_checkpoint_state(cfg.TEST.checkpoints_path) + saver.restore
+        print('Restoring from {}...'.format(weights), end=' ')
+        sess.restore(weights)
+        print('done')
+    except (OSError, KeyError, ValueError) as e:
+        raise SystemExit('Check your pretrained {:s}: {}'.format(str(weights), e))
     im = 128 * np.ones((300, 300, 3), dtype=np.uint8)
     for _ in range(2):                                  # warm-up as demo.py:95-97
         test_ctpn(sess, net, im)

@@ -13,6 +13,8 @@ products); accumulation is always float32.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -58,8 +60,8 @@ class Engine:
 
     # ---- weights -------------------------------------------------------------------------
     def load_weights(self, weights):
-        """weights: dict TF-variable-name -> float32 ndarray, or a path to
-        an .npz with those keys, or a VGG16 .npy dict {layer: {'weights','biases'}} (network.py:40-53)."""
+        """weights: dict TF-variable-name -> float32 ndarray, or a path understood by
+        load_weight_file: TF checkpoint (prefix or directory), frozen .pb, VGG16 .npy dict, .npz."""
         if isinstance(weights, str):
             weights = load_weight_file(weights)
         for name, arr in weights.items():
@@ -305,15 +307,37 @@ class Engine:
         return self.detect_batch(image[None], im_scale)[0]
 
 
+# the 36 variables of the VGGnet_test graph; a TF checkpoint also holds optimizer slots etc.
+REQUIRED_VARIABLES = tuple(
+    ["%s/%s" % (l, k) for l in ("conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1",
+                                "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3", "rpn_conv/3x3")
+     for k in ("weights", "biases")] +
+    ["lstm_o/bidirectional_rnn/%s/lstm_cell/%s" % (d, k) for d in ("fw", "bw") for k in ("kernel", "bias")] +
+    ["%s/%s" % (l, k) for l in ("lstm_o", "rpn_cls_score", "rpn_bbox_pred") for k in ("weights", "biases")])
+
+
 def load_weight_file(path):
-    """.npz with TF variable names, or the reference's VGG .npy dict (network.py:40-53:
-    np.load(..., encoding='latin1').item() -> {layer: {'weights': ..., 'biases': ...}})."""
+    """Weights from what the reference restores from, keyed by TF variable name:
+      * a TF checkpoint V2 -- prefix, `.index` / `.data-*` file, or the directory holding the `checkpoint` state file
+        (ctpn/demo.py:88-90: get_checkpoint_state + saver.restore),
+      * a frozen GraphDef `.pb` (ctpn/generate_pb.py:36-40, ctpn/demo_pb.py),
+      * the VGG `.npy` dict (network.py:40-53: np.load(..., encoding='latin1').item() -> {layer: {'weights', 'biases'}}),
+      * this repo's `.npz` with those variable names.
+    Checkpoints and graphs are reduced to the 36 network variables (a missing one raises KeyError)."""
+    from . import tf_import
     if path.endswith(".npz"):
         with np.load(path) as z:
             return {k: z[k] for k in z.files}
-    d = np.load(path, allow_pickle=True, encoding="latin1").item()
-    out = {}
-    for layer, sub in d.items():
-        for k, v in sub.items():
-            out["%s/%s" % (layer, k)] = np.asarray(v, np.float32)
-    return out
+    if path.endswith(".pb"):
+        return {k: np.asarray(v, np.float32) for k, v in tf_import.read_frozen_graph(path, names=REQUIRED_VARIABLES).items()}
+    if path.endswith(".npy"):
+        d = np.load(path, allow_pickle=True, encoding="latin1").item()
+        out = {}
+        for layer, sub in d.items():
+            for k, v in sub.items():
+                out["%s/%s" % (layer, k)] = np.asarray(v, np.float32)
+        return out
+    prefix = tf_import.checkpoint_prefix(path)
+    if not os.path.isfile(prefix + ".index"):
+        raise FileNotFoundError("%s: not an .npz / .npy / .pb file and no TF checkpoint index at %s.index" % (path, prefix))
+    return {k: np.asarray(v, np.float32) for k, v in tf_import.read_checkpoint(prefix, names=REQUIRED_VARIABLES).items()}
