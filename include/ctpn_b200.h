@@ -146,6 +146,17 @@ int ctpn_net_feature_hw(int H, int W, int *fh, int *fw);
 int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_f32, size_t capacity,
                        size_t *count, void *stream);
 
+/* ---- text lines on the host (replaces lib/text_connector/detectors.py:19-49 and the connector classes) ----
+ * TextDetector.detect in C++ on the CPU: score filter (> 0.7), score order, NMS 0.2, proposal graph
+ * (text_proposal_graph_builder.py:6-78), chains (other.py:16-29), horizontal (oriented = 0,
+ * text_proposal_connector.py:13-64) or oriented (1, text_proposal_connector_oriented.py:24-105) line fitting and
+ * filter_boxes.  proposals [n][4] and scores [n] are test_ctpn()'s output (host memory); lines_out receives
+ * *num_lines rows of 9 doubles (x1,y1,x2,y2,x3,y3,x4,y4,score).  cfg9 = NULL for text_connect_cfg.py's constants, else
+ * (min_score, nms_thresh, max_gap, min_v_overlaps, min_size_sim, min_ratio, line_min_score, proposal_width,
+ * min_num_proposals).  CTPN_ERR_INVALID (with *num_lines set) when more than max_lines lines were found. */
+int ctpn_text_lines_host(const float *proposals, const float *scores, int n, int im_h, int im_w, int oriented,
+                         const float *cfg9, double *lines_out, int max_lines, int *num_lines);
+
 /* ---- diagnostics (not on the product path) ----------------------------------------------
  * Hardware probe used by tests/probe_umma_view.py: reads a [rows][64] bf16 matrix through a UMMA
  * K-major SWIZZLE_128B descriptor that starts at row `row0` with `group_stride_rows` between 8-row

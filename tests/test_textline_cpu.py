@@ -1,0 +1,88 @@
+"""C++ text-line connector (ctpn_text_lines_host, SURVEY.md §8 f rank 3) against the oracle restatement of
+TextDetector.detect and the golden outputs of the reference itself.  Pure host code: runs without a GPU.
+
+Bar: identical line SETS (count and order); every value within 1e-4 px (one float32 ulp at 1000 px is 6e-5) and at
+least 98 % of the values bit-identical -- the rest are 2-box lines, whose end points are evaluated exactly half-way
+between two float32 numbers, where the last bit of LAPACK's double-precision solve decides the rounding in numpy."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from ctpn_b200 import _native as N
+from ctpn_b200.textlines import text_lines
+from oracle import synth, textline
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_postproc.npz"))
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("mode", ["H", "O"])
+def test_matches_reference_goldens(mode):
+    for seed in range(4):
+        tp, sc = synth.make_text_proposals(seed)
+        ref = GOLD["text_%s_%d" % (mode, seed)]
+        got = text_lines(tp, sc, (600, 900), mode)
+        assert got.shape == ref.shape and got.dtype == np.float64
+        assert np.abs(got - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("mode", ["H", "O"])
+def test_matches_oracle_on_many_layouts(mode):
+    total = exact = lines = 0
+    worst = 0.0
+    for seed in range(120):
+        tp, sc = synth.make_text_proposals(100 + seed, n_lines=1 + seed % 14, n_noise=20 + 5 * (seed % 30))
+        ref = textline.detect(tp, sc.reshape(-1, 1), (600, 900), mode)
+        got = text_lines(tp, sc, (600, 900), mode)
+        assert got.shape == ref.shape, "seed %d: %s lines vs %s" % (seed, got.shape, ref.shape)
+        if ref.size:
+            worst = max(worst, float(np.abs(got - ref).max()))
+            total += ref.size
+            exact += int((got == ref).sum())
+            lines += len(ref)
+    print("mode %s: %d lines, %d/%d values bit-exact, max |diff| %.2e" % (mode, lines, exact, total, worst))
+    assert lines > 300 and worst <= TOL and exact >= 0.98 * total
+    np.testing.assert_array_equal(got[:, 8], ref[:, 8]) if ref.size else None     # scores: numpy's pairwise sum, exact
+
+
+def test_other_image_sizes_and_mirror_class():
+    from lib.fast_rcnn.config import cfg
+    from lib.text_connector.detectors import TextDetector
+    tp, sc = synth.make_text_proposals(7, im_h=900, im_w=600, n_lines=9)
+    ref = textline.detect(tp, sc.reshape(-1, 1), (900, 600), "H")
+    old = cfg.TEST.DETECT_MODE
+    try:
+        cfg.TEST.DETECT_MODE = "H"
+        got = TextDetector(native=True).detect(tp, sc.reshape(-1, 1), (900, 600))
+    finally:
+        cfg.TEST.DETECT_MODE = old
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= TOL
+
+
+def test_edge_cases_and_errors():
+    empty = text_lines(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), (600, 900))
+    assert empty.shape == (0, 9)
+    tp, sc = synth.make_text_proposals(2)
+    assert text_lines(tp, np.full_like(sc, 0.5), (600, 900)).shape == (0, 9)          # nothing above 0.7
+    assert text_lines(tp[:1], sc[:1], (600, 900)).shape == (0, 9)                    # a single box is no line
+    with pytest.raises(ValueError):
+        text_lines(tp, sc[:-1], (600, 900))
+    with pytest.raises(ValueError):
+        text_lines(tp, sc, (600, 900), mode="X")
+    with pytest.raises(RuntimeError):                                                # the reference raises IndexError here
+        text_lines(tp, np.full_like(sc, 0.99), (600, 100))
+    # custom constants: with a 0.99 line-score bar no line survives; with no NMS-surviving neighbours within 1 px neither
+    base = (0.7, 0.2, 50, 0.7, 0.7, 0.5, 0.9, 16, 2)
+    assert text_lines(tp, sc, (600, 900), cfg=base).shape == text_lines(tp, sc, (600, 900)).shape
+    assert text_lines(tp, sc, (600, 900), cfg=base[:6] + (0.999,) + base[7:]).shape == (0, 9)
+    assert text_lines(tp, sc, (600, 900), cfg=base[:2] + (1,) + base[3:]).shape == (0, 9)
+    # output buffer too small: status + the number of lines found
+    b = np.ascontiguousarray(tp, np.float32)
+    s = np.ascontiguousarray(sc, np.float32).ravel()
+    out = np.zeros((1, 9))
+    num = C.c_int(0)
+    rc = N.lib.ctpn_text_lines_host(b.ctypes.data, s.ctypes.data, len(s), 600, 900, 0, None, out.ctypes.data, 1, C.byref(num))
+    assert rc != 0 and num.value == len(text_lines(tp, sc, (600, 900))) > 1
+    assert b"lines found" in N.lib.ctpn_last_error()

@@ -30,6 +30,7 @@ from lib.text_connector.detectors import TextDetector   # noqa: E402
 from lib.text_connector.text_connect_cfg import Config as TextLineCfg  # noqa: E402
 
 RESULTS_DIR = "data/results"
+NATIVE_CONNECTOR = False      # --native-connector: C++ text-line connector of the library instead of the Python one
 
 
 def resize_im(im, scale, max_scale=None):
@@ -65,7 +66,7 @@ def ctpn(sess, net, image_name):
     img = cv2.imread(image_name)
     img, scale = resize_im(img, scale=TextLineCfg.SCALE, max_scale=TextLineCfg.MAX_SCALE)
     scores, boxes = test_ctpn(sess, net, img)
-    textdetector = TextDetector()
+    textdetector = TextDetector(native=NATIVE_CONNECTOR)
     boxes = textdetector.detect(boxes, scores[:, np.newaxis], img.shape[:2])
     draw_boxes(img, image_name, boxes, scale)
     timer.toc()
@@ -80,7 +81,11 @@ def main(argv=None):
     ap.add_argument("--planes", type=int, default=2)
     ap.add_argument("--images", default=os.path.join(cfg.DATA_DIR, 'demo', '*'))
     ap.add_argument("--cfg", default=os.path.join(_PKG, 'ctpn', 'text.yml'))
+    ap.add_argument("--native-connector", action="store_true",
+                    help="build the text lines with the library's C++ connector (same lines, float32-rounding agreement)")
     args = ap.parse_args(argv)
+    global NATIVE_CONNECTOR
+    NATIVE_CONNECTOR = args.native_connector
     if os.path.exists(RESULTS_DIR):
         shutil.rmtree(RESULTS_DIR)
     os.makedirs(RESULTS_DIR)
