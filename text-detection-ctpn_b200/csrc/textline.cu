@@ -158,8 +158,10 @@ extern "C" int ctpn_text_lines_host(const float *proposals, const float *scores,
       if (dead[i]) continue;
       tp.push_back(sb[i]);
       sc.push_back(ss[i]);
-      for (size_t j = i + 1; j < sb.size(); ++j)
-        if (!dead[j] && iou_plus1(sb[i], area[i], sb[j], area[j]) > cfg.nms_thresh) dead[j] = 1;
+      for (size_t j = i + 1; j < sb.size(); ++j) {
+        if (dead[j] || sb[j].x1 > sb[i].x2 + 1.0f || sb[j].x2 + 1.0f < sb[i].x1) continue;   // no overlap: IoU = 0
+        if (iou_plus1(sb[i], area[i], sb[j], area[j]) > cfg.nms_thresh) dead[j] = 1;
+      }
     }
   }
   const int m = (int)tp.size();
