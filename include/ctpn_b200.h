@@ -146,6 +146,14 @@ int ctpn_net_feature_hw(int H, int W, int *fh, int *fw);
 int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_f32, size_t capacity,
                        size_t *count, void *stream);
 
+/* ---- image front-end (replaces cv2.resize in resize_im, ctpn/demo.py:21-25) ----
+ * cv2.resize(src, None, None, fx, fy, INTER_LINEAR) for uint8 [B][sh][sw][channels] device images, bit-exact with
+ * OpenCV's fixed-point path (incl. its INTER_AREA routing of an exact 1/2 scale).  ctpn_resize_out_size gives the
+ * destination size cv2 would produce (cvRound(src * f)); dst must have exactly that size. */
+int ctpn_resize_out_size(int sh, int sw, double fx, double fy, int *dh, int *dw);
+int ctpn_resize_linear_u8(const void *src, int B, int sh, int sw, int channels, double fx, double fy, void *dst, int dh,
+                          int dw, void *stream);
+
 /* ---- text lines on the host (replaces lib/text_connector/detectors.py:19-49 and the connector classes) ----
  * TextDetector.detect in C++ on the CPU: score filter (> 0.7), score order, NMS 0.2, proposal graph
  * (text_proposal_graph_builder.py:6-78), chains (other.py:16-29), horizontal (oriented = 0,

@@ -175,12 +175,17 @@ class Engine:
         return gather_results(rois, count)
 
     def rois_batch(self, images, im_info=None, gather=False):
-        """images: host ndarray or (pinned) CPU tensor [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
+        """images: host ndarray, (pinned) CPU tensor or device tensor [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
         im_info: [B,3] (defaults to (H, W, 1.0)).  Returns one float32 [n,5] array per image,
         rows (score, x1, y1, x2, y2) in blob coordinates -- the 'rois' tensor of the reference
         graph (network.py:217).  H2D of the inputs and D2H of the results are part of the call.
         gather=True (multi-GPU): results of all ranks' shards, in rank order."""
-        if isinstance(images, torch.Tensor):
+        if isinstance(images, torch.Tensor) and images.device.type == "cuda":
+            # already resident (e.g. the output of resize_images): no staging, no H2D
+            assert images.dtype in (torch.uint8, torch.float32)
+            B, H, W, _ = images.shape
+            stage = images.contiguous()
+        elif isinstance(images, torch.Tensor):
             # a pinned host tensor is transferred as is (no staging copy)
             assert images.device.type == "cpu" and images.dtype in (torch.uint8, torch.float32)
             B, H, W, _ = images.shape
@@ -301,6 +306,36 @@ class Engine:
                 for i, r in zip(part, res):
                     out[i] = r
         return out
+
+    def resize_images(self, images, fx, fy=None):
+        """cv2.resize(im, None, None, fx=fx, fy=fy, interpolation=cv2.INTER_LINEAR) of a uint8 batch [B,H,W,C] on the
+        device (bit-exact with OpenCV; resize_im of ctpn/demo.py:21-25).  images: ndarray or torch tensor (host or
+        device); returns a uint8 device tensor [B,dh,dw,C]."""
+        fy = fx if fy is None else fy
+        t = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        if t.dtype != torch.uint8 or t.dim() != 4:
+            raise ValueError("resize_images expects a uint8 [B,H,W,C] batch")
+        t = t.to(self.device, non_blocking=True).contiguous()
+        B, H, W, Cn = t.shape
+        dh, dw = C.c_int(0), C.c_int(0)
+        N.check(N.lib.ctpn_resize_out_size(H, W, float(fx), float(fy), C.byref(dh), C.byref(dw)), "ctpn_resize_out_size")
+        out = torch.empty((B, dh.value, dw.value, Cn), dtype=torch.uint8, device=self.device)
+        N.check(N.lib.ctpn_resize_linear_u8(N.ptr(t), B, H, W, Cn, float(fx), float(fy), N.ptr(out), dh.value, dw.value,
+                                            N.stream_ptr()), "ctpn_resize_linear_u8")
+        return out
+
+    def detect_resized(self, images, scale=600, max_scale=1200):
+        """The front half of ctpn() (demo.py:59-61) for a same-shape uint8 batch: resize_im on the device (short side
+        -> scale, long side <= max_scale), then the detector.  Returns ([(scores, boxes)], f); boxes are in the resized
+        frame, as TextDetector expects them (draw_boxes divides by f).  Assumes the resized long side is within
+        cfg.TEST.MAX_SIZE so that _get_image_blob adds no second rescale (true for the default 600 / 1200 / 1000
+        settings whenever the aspect ratio is <= 5:3)."""
+        H, W = int(images.shape[1]), int(images.shape[2])
+        f = float(scale) / min(H, W)
+        if max_scale is not None and f * max(H, W) > max_scale:
+            f = float(max_scale) / max(H, W)
+        resized = images if f == 1.0 else self.resize_images(images, f)
+        return self.detect_batch(resized), f
 
     def detect(self, image, im_scale=1.0):
         """Single image [H,W,3] -> (scores, boxes); the test_ctpn() contract."""
