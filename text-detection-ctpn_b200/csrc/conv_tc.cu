@@ -15,13 +15,14 @@
 //   * D: float32 accumulators in TMEM; tcgen05.mma issued by one thread, completion via tcgen05.commit.
 //     With P > 1 planes the plane-0 x plane-0 products go to a "main" accumulator and all cross-plane
 //     products to a second one (the tensor core truncates when adding into float32).
-//   * epilogue (4 warps = 128 TMEM lanes): tcgen05.ld -> (+cross) -> +bias -> ReLU -> optional fused 2x2
-//     max-pool (warp shuffles: the window of a pixel lives in lanes l, l^1, l^8, l^9) -> re-split into
-//     planes -> 16-byte global stores (or float32 output).
+//   * epilogue (2 x 4 warps; a set covers the 128 TMEM lanes and takes every other 32-column chunk): tcgen05.ld ->
+//     (+cross) -> +bias -> ReLU -> optional fused 2x2 max-pool (warp shuffles: the window of a pixel lives in lanes
+//     l, l^1, l^8, l^9) -> re-split into planes (cvt.rn.bf16x2.f32) -> transpose through swizzled shared memory ->
+//     16-byte stores that cover one pixel's 64 contiguous bytes with 4 lanes (or float32 output).
 // 3x3 layers run as 2-CTA clusters that share every weight tile by TMA multicast (template parameter MC; CTPN_TC_MCAST=0
 // selects the single-CTA variant): -2.4 % (bf16x2) / -2.8 % (bf16) conv time in a same-box A/B.
 // Persistent CTAs (one per SM), warp-specialised: warp 0 weight (B) producer, warp 1 MMA issuer + TMEM
-// owner, warps 2-5 epilogue, warp 6 activation (A) producer.  Reference: lib/networks/network.py:160-196.
+// owner, warps 2-5 and 7-10 epilogue, warp 6 activation (A) producer.  Reference: lib/networks/network.py:160-196.
 #include <cuda.h>
 
 #include <algorithm>
