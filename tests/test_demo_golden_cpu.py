@@ -34,3 +34,30 @@ def test_resize_im_matches_reference(k):
     assert f == float(GOLD["resize_f_%d" % k]) == R.resize_im_scale(h, w, 120, 240)
     np.testing.assert_array_equal(out, GOLD["resize_out_%d" % k])
     np.testing.assert_array_equal(R.resize_linear_u8(im, f), GOLD["resize_out_%d" % k])   # the oracle, without cv2 in the loop
+
+
+BLOB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_image_blob.npz"))
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_get_image_blob_matches_reference(k):
+    """lib/fast_rcnn/test.py mirror against the reference's _get_image_blob (tests/golden/make_golden_blob.py), with the
+    same reduced TEST.SCALES / MAX_SIZE.  At scale 1 the mirror hands the uint8 image through (conv1_1 subtracts the
+    means on the device as float32(double(v) - mean)); that arithmetic must reproduce the reference blob bit for bit."""
+    from lib.fast_rcnn.config import cfg
+    from lib.fast_rcnn import test as T
+    old = cfg.TEST.SCALES, cfg.TEST.MAX_SIZE
+    try:
+        cfg.TEST.SCALES, cfg.TEST.MAX_SIZE = tuple(int(v) for v in BLOB["scales"]), int(BLOB["max_size"])
+        h, w = [int(v) for v in BLOB["shape_%d" % k]]
+        im = np.random.RandomState(300 + k).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        blob, factors = T._get_image_blob(im)
+    finally:
+        cfg.TEST.SCALES, cfg.TEST.MAX_SIZE = old
+    np.testing.assert_array_equal(factors, BLOB["factors_%d" % k])
+    ref = BLOB["blob_%d" % k]
+    if blob.dtype == np.uint8:
+        assert factors[0] == 1.0
+        blob = (blob.astype(np.float64) - np.asarray(cfg.PIXEL_MEANS, np.float64)).astype(np.float32)
+    assert blob.dtype == np.float32 and blob.shape == ref.shape
+    np.testing.assert_array_equal(blob, ref)
