@@ -86,3 +86,32 @@ def test_edge_cases_and_errors():
     rc = N.lib.ctpn_text_lines_host(b.ctypes.data, s.ctypes.data, len(s), 600, 900, 0, None, out.ctypes.data, 1, C.byref(num))
     assert rc != 0 and num.value == len(text_lines(tp, sc, (600, 900))) > 1
     assert b"lines found" in N.lib.ctpn_last_error()
+
+
+def test_fuzz_random_layouts_sizes_and_ties():
+    """Unstructured inputs: arbitrary image sizes, float x1 (not column aligned), clustered rows, tied scores.  The line
+    SETS must agree exactly; coordinates within 2 float32 ulp at the largest coordinate (1700 px -> 2.5e-4)."""
+    rs = np.random.RandomState(123)
+    lines = 0
+    for t in range(200):
+        h, w = int(rs.randint(100, 1300)), int(rs.randint(100, 1700))
+        n = int(rs.randint(0, 300))
+        x1 = rs.uniform(0, w - 17, n) if rs.rand() < 0.5 else 16.0 * rs.randint(0, (w - 17) // 16 + 1, n)
+        yc, hh = rs.uniform(10, h - 10, n), rs.uniform(6, 80, n)
+        if rs.rand() < 0.6 and n:
+            rows = rs.uniform(20, h - 20, max(1, n // 20))
+            yc, hh = rows[rs.randint(0, len(rows), n)] + rs.normal(0, 2, n), 20 + rs.normal(0, 1.5, n)
+        b = np.stack([x1, yc - hh / 2, x1 + 16, yc + hh / 2], 1).astype(np.float32)
+        b[:, 0::2] = np.clip(b[:, 0::2], 0, w - 1)
+        b[:, 1::2] = np.clip(b[:, 1::2], 0, h - 1)
+        s = rs.uniform(0.6, 1.0, n).astype(np.float32)
+        if rs.rand() < 0.3:
+            s = np.round(s, 2).astype(np.float32)
+        for mode in ("H", "O"):
+            ref = textline.detect(b, s.reshape(-1, 1), (h, w), mode)
+            got = text_lines(b, s, (h, w), mode)
+            assert got.shape == ref.shape, (t, mode)
+            if ref.size:
+                assert np.abs(got - ref).max() <= 3e-4, (t, mode)
+                lines += len(ref)
+    assert lines > 200
