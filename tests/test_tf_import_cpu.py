@@ -124,3 +124,15 @@ def test_load_weight_file_dispatch(tmp_path):
     os.remove(prefix + ".index")
     with pytest.raises((FileNotFoundError, OSError)):
         load_weight_file(prefix)
+
+
+def test_command_line_list_and_convert(tmp_path, capsys):
+    w = {"a/weights": np.arange(6, dtype=np.float32).reshape(2, 3), "global_step": np.asarray(3, np.int64)}
+    prefix = str(tmp_path / "m.ckpt")
+    W.write_checkpoint(prefix, w)
+    assert T._main([prefix]) == 0
+    out = capsys.readouterr().out
+    assert "a/weights" in out and "(2, 3)" in out and "global_step" in out
+    assert T._main([str(tmp_path), str(tmp_path / "w.npz")]) == 0
+    with np.load(str(tmp_path / "w.npz")) as z:
+        np.testing.assert_array_equal(z["a/weights"], w["a/weights"])

@@ -418,3 +418,25 @@ def read_frozen_graph(path, names=None):
             if n not in out:
                 raise KeyError("constant '%s' is not in graph %s" % (n, path))
     return out
+
+
+def _main(argv=None):
+    """python -m ctpn_b200.tf_import <checkpoint prefix | directory | frozen.pb> [out.npz]
+    Lists the tensors of a TF checkpoint / frozen graph, or converts them to an .npz keyed by variable name."""
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m ctpn_b200.tf_import", description=_main.__doc__)
+    ap.add_argument("source")
+    ap.add_argument("out", nargs="?", help=".npz to write (omit to list)")
+    a = ap.parse_args(argv)
+    tensors = read_frozen_graph(a.source) if a.source.endswith(".pb") else read_checkpoint(a.source)
+    if a.out:
+        np.savez(a.out, **tensors)
+        print("wrote %d tensors to %s" % (len(tensors), a.out))
+    else:
+        for k in sorted(tensors):
+            print("%-60s %-8s %s" % (k, tensors[k].dtype, tuple(tensors[k].shape)))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())
