@@ -165,6 +165,18 @@ int ctpn_resize_linear_u8(const void *src, int B, int sh, int sw, int channels, 
 int ctpn_text_lines_host(const float *proposals, const float *scores, int n, int im_h, int im_w, int oriented,
                          const float *cfg9, double *lines_out, int max_lines, int *num_lines);
 
+/* The stages of ctpn_text_lines_host for callers that fit the lines themselves (the Python TextDetector mirror fits with
+ * numpy so that np.polyfit's own LAPACK solve produces the coordinates).
+ * ctpn_text_filter_nms_host: detectors.py:21-28 -- score filter, score order (index ascending on ties), greedy NMS;
+ * keep_out[n] receives *num_keep indices into the input, in visiting order.
+ * ctpn_text_groups_host: graph + chain walk over m proposals in the given order (what get_text_lines receives);
+ * chain g = members[offsets[g] .. offsets[g+1]), offsets[m+1].  Chains that run into the same successor share their
+ * tails, so *num_members can exceed m: CTPN_ERR_WORKSPACE (with *num_members set) when members_capacity is too small. */
+int ctpn_text_filter_nms_host(const float *proposals, const float *scores, int n, const float *cfg9, int *keep_out,
+                              int *num_keep);
+int ctpn_text_groups_host(const float *proposals, const float *scores, int m, int im_w, const float *cfg9, int *offsets,
+                          int *members, int members_capacity, int *num_groups, int *num_members);
+
 /* ---- diagnostics (not on the product path) ----------------------------------------------
  * Hardware probe used by tests/probe_umma_view.py: reads a [rows][64] bf16 matrix through a UMMA
  * K-major SWIZZLE_128B descriptor that starts at row `row0` with `group_stride_rows` between 8-row

@@ -52,7 +52,6 @@ def test_image_blob_decisions_match_reference_rules():
 def test_text_detector_host_code_matches_reference_goldens(mode, monkeypatch):
     import lib.text_connector.detectors as det
     from lib.fast_rcnn.config import cfg
-    monkeypatch.setattr(det, "nms", postproc.nms)
     monkeypatch.setattr(cfg.TEST, "DETECT_MODE", mode, raising=False)
     cfg.TEST.DETECT_MODE = mode
     try:
@@ -66,16 +65,28 @@ def test_text_detector_host_code_matches_reference_goldens(mode, monkeypatch):
 
 def test_text_detector_empty_and_single():
     import lib.text_connector.detectors as det
-    d = det.TextDetector()
-    d_nms = det.nms
-    det.nms = postproc.nms
-    try:
-        out = d.detect(np.zeros((0, 4), np.float32), np.zeros((0, 1), np.float32), (600, 900))
-        assert out.shape == (0, 9)
-        out = d.detect(np.array([[16, 10, 32, 40]], np.float32), np.array([[0.99]], np.float32), (600, 900))
-        assert out.shape == (0, 9)                          # a lone proposal forms no line
-    finally:
-        det.nms = d_nms
+    d = det.TextDetector()                                  # the whole of detect() is host code: no GPU needed
+    out = d.detect(np.zeros((0, 4), np.float32), np.zeros((0, 1), np.float32), (600, 900))
+    assert out.shape == (0, 9)
+    out = d.detect(np.array([[16, 10, 32, 40]], np.float32), np.array([[0.99]], np.float32), (600, 900))
+    assert out.shape == (0, 9)                          # a lone proposal forms no line
+
+
+def test_connector_stages_match_python_graph_builder():
+    """The C++ grouping (ctpn_text_groups_host) against the vectorised Python graph builder kept in the mirror, and the
+    host NMS (ctpn_text_filter_nms_host) against the oracle's NMS, on the synthetic layouts."""
+    from ctpn_b200 import textlines
+    from lib.text_connector.text_proposal_graph_builder import TextProposalGraphBuilder
+    for seed in range(30):
+        tp, sc = synth.make_text_proposals(300 + seed, n_lines=2 + seed % 9, n_noise=40 + 7 * seed)
+        keep = textlines.filter_nms(tp, sc)
+        sel = np.where(sc.ravel() > 0.7)[0]
+        order = sel[np.argsort(-sc.ravel()[sel], kind="stable")]
+        want = order[postproc.nms(np.hstack((tp[order], sc[order])), 0.2)]
+        np.testing.assert_array_equal(keep, want)
+        got = textlines.groups(tp[keep], sc[keep], (600, 900))
+        ref = TextProposalGraphBuilder().build_graph(tp[keep], sc[keep], (600, 900)).sub_graphs_connected()
+        assert got == [list(map(int, c)) for c in ref]
 
 
 def test_draw_boxes_writes_reference_format(tmp_path, monkeypatch):

@@ -47,6 +47,53 @@ def test_matches_oracle_on_many_layouts(mode):
     np.testing.assert_array_equal(got[:, 8], ref[:, 8]) if ref.size else None     # scores: numpy's pairwise sum, exact
 
 
+def _round_f32(fr):
+    """Correctly rounded (nearest, ties to even) float32 of an exact Fraction."""
+    from fractions import Fraction
+    x = np.float32(float(fr))                 # double rounding is harmless here: candidates are checked exactly below
+    lo, hi = np.nextafter(x, np.float32(-np.inf)), np.nextafter(x, np.float32(np.inf))
+    best = min((lo, x, hi), key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
+    return np.float32(best)
+
+
+def test_native_fit_is_the_correctly_rounded_exact_fit_on_two_box_lines():
+    """Where the all-C++ path and numpy's np.polyfit disagree (1 float32 ulp), the C++ value is the correctly rounded
+    exact least-squares result and numpy's is not: for a 2-box chain the fitted line passes through both points, so the
+    exact value at x is a rational number; it is checked here with fractions.Fraction."""
+    from fractions import Fraction
+    from ctpn_b200 import textlines
+    checked = ties = numpy_off = 0
+    for seed in range(120):
+        tp, sc = synth.make_text_proposals(100 + seed, n_lines=1 + seed % 14, n_noise=20 + 5 * (seed % 30))
+        keep = textlines.filter_nms(tp, sc)
+        b, s = tp[keep], sc[keep]
+        chains = textlines.groups(b, s, (600, 900))
+        two = [c for c in chains if len(c) == 2 and b[c[0], 0] != b[c[1], 0]]
+        if not two:
+            continue
+        native = textlines.text_lines(b, s, (600, 900), "H", (0.0, 2.0, 50, 0.7, 0.7, 0.0, 0.0, 0, 0))   # filters off: every chain comes back
+        via_np = textlines.fit_lines(b, s, chains, (600, 900), "H")
+        assert native.shape == via_np.shape == (len(chains), 9)
+        for c in two:
+            row = chains.index(c)
+            g = b[c]
+            left, right = g[:, 0].min(), g[:, 2].max()
+            half = (g[0, 2] - g[0, 0]) * np.float32(0.5)
+            xa, xb = Fraction(float(left + half)), Fraction(float(right - half))
+            for col, ycol in ((1, 1), (5, 3)):                       # top edge -> min, bottom edge -> max
+                x0, x1, y0, y1 = (Fraction(float(v)) for v in (g[0, 0], g[1, 0], g[0, ycol], g[1, ycol]))
+                ends = [y0 + (y1 - y0) * (x - x0) / (x1 - x0) for x in (xa, xb)]
+                exact = min(ends) if col == 1 else max(ends)
+                want = _round_f32(exact)
+                want = np.float32(min(max(want, np.float32(0)), np.float32(599)))
+                assert np.float32(native[row, col]) == want, (seed, c, col)
+                checked += 1
+                ties += int(Fraction(float(want)) != exact and abs(Fraction(float(want)) - exact) * 2 == Fraction(float(np.spacing(want))))
+                numpy_off += int(np.float32(via_np[row, col]) != want)
+    print("2-box edges checked %d, exact float32 ties %d, numpy != correctly rounded %d" % (checked, ties, numpy_off))
+    assert checked > 100
+
+
 def test_other_image_sizes_and_mirror_class():
     from lib.fast_rcnn.config import cfg
     from lib.text_connector.detectors import TextDetector

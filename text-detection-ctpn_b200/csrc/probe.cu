@@ -224,6 +224,124 @@ probe_mma_rate_pair_kernel(int n_mma, int alternate_acc) {
 
 }  // namespace ctpn
 
+// ---- probe 3: dispatch rate of kind::f8f6f4 (e4m3, K = 32 per instruction) next to kind::f16 (K = 16), from one CTA
+// (M = 128) or a CTA pair (cta_group::2, M = 256).  mode 0: all f16; 1: all f8; 2: groups of 4 f16 -> accumulator 0 followed
+// by 4 f8 -> accumulator 1 (the issue pattern of a "fp16 main + fp8 cross" convolution step).  Same operand bytes per
+// instruction for both kinds (128 rows x 32 B of A), so the comparison isolates the tensor-pipe rate.
+namespace ctpn {
+
+__host__ __device__ constexpr uint32_t umma_idesc_e4m3(int M, int N) {   // kind::f8f6f4: A = B = E4M3 (format code 0), D = f32
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int PAIR>
+__global__ void __launch_bounds__(128, 1)
+probe_mma_kind_kernel(int n_mma, int mode) {
+  using namespace ptx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sa = (raw + 1023u) & ~1023u, sb = sa + 16384;
+  constexpr int kBRows = PAIR ? BN / 2 : BN;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < (16384 + kBRows * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem_raw + (sa - raw))[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x < 32) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(smem_u32(&tmem_slot), 512);
+      tmem_relinquish();
+    }
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const bool leader = !PAIR || cluster_ctarank() == 0;
+  if (__shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) == 0) {
+    if (leader) {
+      constexpr int M = PAIR ? 256 : 128;
+      const uint32_t id16 = umma_idesc_bf16(M, BN), id8 = umma_idesc_e4m3(M, BN);
+      const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+      const uint32_t acc1 = (2 * BN <= 512) ? (uint32_t)BN : 0u;
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const bool f8 = mode == 1 || (mode == 2 && (u & 4));
+            const uint32_t d = tmem + ((mode == 2 && (u & 4)) ? acc1 : 0u);
+            const uint32_t acc = (i | u) > 7;
+            const uint64_t a = da + 2ull * (u & 3), b = db + 2ull * (u & 3);
+            if (PAIR) {
+              if (f8) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                                   ::"r"(d), "l"(a), "l"(b), "r"(id8), "r"(acc) : "memory");
+              else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(d), "l"(a), "l"(b), "r"(id16), "r"(acc) : "memory");
+            } else {
+              if (f8) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                                   ::"r"(d), "l"(a), "l"(b), "r"(id8), "r"(acc) : "memory");
+              else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(d), "l"(a), "l"(b), "r"(id16), "r"(acc) : "memory");
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        if (PAIR) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                               ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        else mma_commit(smem_u32(&bar));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), 0);
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    else tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace ctpn
+
+extern "C" int ctpn_probe_mma_kind(int bn, int pair, int mode, int n_mma, int grid, void *stream) {
+  CTPN_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ctpn_probe_mma_kind: bn must be 64/128/256");
+  CTPN_REQUIRE(n_mma > 0 && n_mma % 8 == 0 && grid > 0 && mode >= 0 && mode <= 2, "ctpn_probe_mma_kind: bad arguments");
+  CTPN_REQUIRE(!pair || grid % 2 == 0, "ctpn_probe_mma_kind: pair mode needs an even grid");
+  const size_t smem = 1024 + 16384 + (size_t)bn * (pair ? 64 : 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CTPN_LAUNCH_KIND(BN, PAIR)                                                                                 \
+  do {                                                                                                             \
+    auto k = probe_mma_kind_kernel<BN, PAIR>;                                                                      \
+    CTPN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    cudaLaunchConfig_t cfg = {};                                                                                   \
+    cudaLaunchAttribute attr;                                                                                      \
+    attr.id = cudaLaunchAttributeClusterDimension;                                                                 \
+    attr.val.clusterDim.x = PAIR ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;                    \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;              \
+    cfg.attrs = &attr; cfg.numAttrs = 1;                                                                           \
+    CTPN_CUDA(cudaLaunchKernelEx(&cfg, k, n_mma, mode));                                                           \
+  } while (0)
+  if (pair) {
+    if (bn == 256) CTPN_LAUNCH_KIND(256, 1); else if (bn == 128) CTPN_LAUNCH_KIND(128, 1); else CTPN_LAUNCH_KIND(64, 1);
+  } else {
+    if (bn == 256) CTPN_LAUNCH_KIND(256, 0); else if (bn == 128) CTPN_LAUNCH_KIND(128, 0); else CTPN_LAUNCH_KIND(64, 0);
+  }
+#undef CTPN_LAUNCH_KIND
+  CTPN_LAUNCH_CHECK();
+  return CTPN_OK;
+}
+
 extern "C" int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
                                    int grid, void *stream) {
   CTPN_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ctpn_probe_mma_rate: bn must be 64/128/256");

@@ -113,61 +113,66 @@ void fit_y(const std::vector<float> &X, const std::vector<float> &Y, float x1, f
     y1 = y2 = (double)Y[0];
     return;
   }
+  if (X.size() == 2) {
+    // two boxes: the least-squares line passes through both points.  Evaluated as an interpolation in double, every
+    // step is exact for float32 inputs in the connector's geometry (abscissa ratio 8/16, 24/16, ...), so the stored
+    // float32 value is the correctly rounded exact fit; numpy's LAPACK result carries ~1e-16 of noise, which decides
+    // the rounding when the exact value is a float32 tie (the mean of two adjacent-parity ordinates).
+    const double xa = X[0], xb = X[1], ya = Y[0], yb = Y[1];
+    y1 = ya + (yb - ya) * (((double)x1 - xa) / (xb - xa));
+    y2 = ya + (yb - ya) * (((double)x2 - xa) / (xb - xa));
+    return;
+  }
   double m, c;
   polyfit1(X, Y, m, c);
   y1 = m * (double)x1 + c;
   y2 = m * (double)x2 + c;
 }
 
-}  // namespace
-}  // namespace ctpn
-
-using namespace ctpn;
-
-extern "C" int ctpn_text_lines_host(const float *proposals, const float *scores, int n, int im_h, int im_w, int oriented,
-                                    const float *cfg9, double *lines_out, int max_lines, int *num_lines) {
-  CTPN_REQUIRE(num_lines && (n == 0 || (proposals && scores)), "ctpn_text_lines_host: null pointer");
-  CTPN_REQUIRE(n >= 0 && im_h > 0 && im_w > 0 && max_lines >= 0, "ctpn_text_lines_host: bad arguments");
-  CTPN_REQUIRE(max_lines == 0 || lines_out, "ctpn_text_lines_host: null output");
+TextCfg parse_cfg(const float *cfg9) {
   TextCfg cfg;
   if (cfg9) {   // (min_score, nms_thresh, max_gap, min_v_overlaps, min_size_sim, min_ratio, line_min_score, width, min_num)
     cfg.min_score = cfg9[0]; cfg.nms_thresh = cfg9[1]; cfg.max_gap = (int)cfg9[2]; cfg.min_v_overlaps = cfg9[3];
     cfg.min_size_sim = cfg9[4]; cfg.min_ratio = (double)cfg9[5]; cfg.line_min_score = (double)cfg9[6];
     cfg.proposal_width = (int)cfg9[7]; cfg.min_num_proposals = (int)cfg9[8];
   }
-  *num_lines = 0;
-  // detectors.py:21-26: score filter, then score-descending order (index ascending on ties)
+  return cfg;
+}
+
+// detectors.py:21-28: score filter, score-descending order (index ascending on ties), greedy NMS (IoU with the +1
+// convention, strict >).  Returns the surviving input indices in visiting order.
+std::vector<int> filter_sort_nms(const float *proposals, const float *scores, int n, const TextCfg &cfg) {
   std::vector<int> order;
   for (int i = 0; i < n; ++i)
     if (scores[i] > cfg.min_score) order.push_back(i);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return scores[a] > scores[b]; });
   std::vector<Box> sb(order.size());
-  std::vector<float> ss(order.size()), area(order.size());
+  std::vector<float> area(order.size());
   for (size_t k = 0; k < order.size(); ++k) {
     const float *p = proposals + 4 * (size_t)order[k];
     sb[k] = {p[0], p[1], p[2], p[3]};
-    ss[k] = scores[order[k]];
     area[k] = (p[2] - p[0] + 1.0f) * (p[3] - p[1] + 1.0f);
   }
-  // detectors.py:27-28: greedy NMS (IoU with the +1 convention, strict >)
-  std::vector<Box> tp;
-  std::vector<float> sc;
-  {
-    std::vector<char> dead(sb.size(), 0);
-    for (size_t i = 0; i < sb.size(); ++i) {
-      if (dead[i]) continue;
-      tp.push_back(sb[i]);
-      sc.push_back(ss[i]);
-      for (size_t j = i + 1; j < sb.size(); ++j) {
-        if (dead[j] || sb[j].x1 > sb[i].x2 + 1.0f || sb[j].x2 + 1.0f < sb[i].x1) continue;   // no overlap: IoU = 0
-        if (iou_plus1(sb[i], area[i], sb[j], area[j]) > cfg.nms_thresh) dead[j] = 1;
-      }
+  std::vector<int> keep;
+  std::vector<char> dead(sb.size(), 0);
+  for (size_t i = 0; i < sb.size(); ++i) {
+    if (dead[i]) continue;
+    keep.push_back(order[i]);
+    for (size_t j = i + 1; j < sb.size(); ++j) {
+      if (dead[j] || sb[j].x1 > sb[i].x2 + 1.0f || sb[j].x2 + 1.0f < sb[i].x1) continue;   // no overlap: IoU = 0
+      if (iou_plus1(sb[i], area[i], sb[j], area[j]) > cfg.nms_thresh) dead[j] = 1;
     }
   }
+  return keep;
+}
+
+// Proposal graph (text_proposal_graph_builder.py:56-78) and its chains (other.py:16-29) over m proposals in the order
+// given.  next[i] = successor of i or -1; a chain starts at every node with a successor and no predecessor.
+int build_chains(const std::vector<Box> &tp, const std::vector<float> &sc, int im_w, const TextCfg &cfg,
+                 std::vector<int> &next, std::vector<char> &has_in) {
   const int m = (int)tp.size();
-  // ---- graph (text_proposal_graph_builder.py:56-78) ----
   for (int i = 0; i < m; ++i)
-    CTPN_REQUIRE(tp[i].x1 >= 0.f && (int)tp[i].x1 < im_w, "ctpn_text_lines_host: proposal x1=%g outside the image width %d",
+    CTPN_REQUIRE(tp[i].x1 >= 0.f && (int)tp[i].x1 < im_w, "text lines: proposal x1=%g outside the image width %d",
                  (double)tp[i].x1, im_w);   // the reference would raise IndexError on boxes_table[int(x1)]
   std::vector<float> heights(m);
   std::vector<std::vector<int>> table(im_w);
@@ -204,8 +209,8 @@ extern "C" int ctpn_text_lines_host(const float *proposals, const float *scores,
     }
     hits.clear();
   };
-  std::vector<int> next(m, -1);
-  std::vector<char> has_in(m, 0);
+  next.assign(m, -1);
+  has_in.assign(m, 0);
   for (int i = 0; i < m; ++i) {
     successions(i);
     if (hits.empty()) continue;
@@ -220,6 +225,81 @@ extern "C" int ctpn_text_lines_host(const float *proposals, const float *scores,
       has_in[s] = 1;
     }
   }
+  return CTPN_OK;
+}
+
+
+}  // namespace
+}  // namespace ctpn
+
+using namespace ctpn;
+
+extern "C" int ctpn_text_filter_nms_host(const float *proposals, const float *scores, int n, const float *cfg9,
+                                         int *keep_out, int *num_keep) {
+  CTPN_REQUIRE(num_keep && (n == 0 || (proposals && scores && keep_out)), "ctpn_text_filter_nms_host: null pointer");
+  CTPN_REQUIRE(n >= 0, "ctpn_text_filter_nms_host: bad arguments");
+  const TextCfg cfg = parse_cfg(cfg9);
+  const std::vector<int> keep = filter_sort_nms(proposals, scores, n, cfg);
+  *num_keep = (int)keep.size();
+  if (!keep.empty()) memcpy(keep_out, keep.data(), keep.size() * sizeof(int));
+  return CTPN_OK;
+}
+
+extern "C" int ctpn_text_groups_host(const float *proposals, const float *scores, int m, int im_w, const float *cfg9,
+                                     int *offsets, int *members, int members_capacity, int *num_groups, int *num_members) {
+  CTPN_REQUIRE(num_groups && num_members && offsets && (m == 0 || (proposals && scores)), "ctpn_text_groups_host: null pointer");
+  CTPN_REQUIRE(m >= 0 && im_w > 0 && members_capacity >= 0 && (members || members_capacity == 0), "ctpn_text_groups_host: bad arguments");
+  const TextCfg cfg = parse_cfg(cfg9);
+  std::vector<Box> tp(m);
+  std::vector<float> sc(scores, scores + m);
+  for (int i = 0; i < m; ++i) tp[i] = {proposals[4 * i], proposals[4 * i + 1], proposals[4 * i + 2], proposals[4 * i + 3]};
+  std::vector<int> next;
+  std::vector<char> has_in;
+  int rc = build_chains(tp, sc, im_w, cfg, next, has_in);
+  if (rc) return rc;
+  // chains that run into the same successor share their tails (other.py:16-29 walks every head to the end), so the
+  // total member count can exceed m
+  int g = 0;
+  long long k = 0;
+  offsets[0] = 0;
+  for (int i = 0; i < m; ++i) {
+    if (has_in[i] || next[i] < 0) continue;
+    int guard = 0;
+    for (int v = i; v >= 0 && guard <= m; v = next[v], ++guard) {
+      if (k < members_capacity) members[k] = v;
+      ++k;
+    }
+    offsets[++g] = (int)std::min<long long>(k, 0x7fffffff);
+  }
+  *num_groups = g;
+  *num_members = (int)std::min<long long>(k, 0x7fffffff);
+  if (k > members_capacity) {
+    set_error("ctpn_text_groups_host: %lld chain members, room for %d", k, members_capacity);
+    return CTPN_ERR_WORKSPACE;
+  }
+  return CTPN_OK;
+}
+
+extern "C" int ctpn_text_lines_host(const float *proposals, const float *scores, int n, int im_h, int im_w, int oriented,
+                                    const float *cfg9, double *lines_out, int max_lines, int *num_lines) {
+  CTPN_REQUIRE(num_lines && (n == 0 || (proposals && scores)), "ctpn_text_lines_host: null pointer");
+  CTPN_REQUIRE(n >= 0 && im_h > 0 && im_w > 0 && max_lines >= 0, "ctpn_text_lines_host: bad arguments");
+  CTPN_REQUIRE(max_lines == 0 || lines_out, "ctpn_text_lines_host: null output");
+  const TextCfg cfg = parse_cfg(cfg9);
+  *num_lines = 0;
+  const std::vector<int> keep = filter_sort_nms(proposals, scores, n, cfg);
+  const int m = (int)keep.size();
+  std::vector<Box> tp(m);
+  std::vector<float> sc(m);
+  for (int k = 0; k < m; ++k) {
+    const float *p = proposals + 4 * (size_t)keep[k];
+    tp[k] = {p[0], p[1], p[2], p[3]};
+    sc[k] = scores[keep[k]];
+  }
+  std::vector<int> next;
+  std::vector<char> has_in;
+  int rc = build_chains(tp, sc, im_w, cfg, next, has_in);
+  if (rc) return rc;
   // ---- chains (other.py:16-29) and lines ----
   std::vector<double> recs;   // 9 doubles per line
   std::vector<float> X, Yt, Yb, S, Hh, Xc, Yc;

@@ -15,6 +15,9 @@ class CtpnError(RuntimeError):
     pass
 
 
+ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_NO_DEVICE = 1, 2, 3, 4     # include/ctpn_b200.h
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "libctpn_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -36,6 +39,8 @@ SIGNATURES = {
     "ctpn_prof_report": (_i, [_p, _z, C.POINTER(_z)]),
     "ctpn_nms_host": (_i, [_p, _p, _p, _i, _i, _f, _i]),
     "ctpn_text_lines_host": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "ctpn_text_filter_nms_host": (_i, [_p, _p, _i, _p, _p, _p]),
+    "ctpn_text_groups_host": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p]),
     "ctpn_resize_out_size": (_i, [_i, _i, C.c_double, C.c_double, _p, _p]),
     "ctpn_resize_linear_u8": (_i, [_p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _i, _i, _p]),
     "ctpn_nms_workspace_bytes": (_z, [_i, _i]),

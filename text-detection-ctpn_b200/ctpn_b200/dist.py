@@ -12,13 +12,25 @@ def shard_range(n_images, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def gather_packed(packed):
+    """packed: this rank's result buffer [L] float32 (rois followed by the int32 counts' bit patterns, see
+    Engine.detect_packed) -> [world, L] in rank order.  ONE collective per batch.  Issued on the caller's current
+    stream (Engine.rois_batches calls it on its result stream, off the compute stream)."""
+    world = dist.get_world_size()
+    packed = packed.contiguous()
+    out = torch.empty((world * packed.numel(),), dtype=packed.dtype, device=packed.device)   # flat: gloo wants [world * L]
+    dist.all_gather_into_tensor(out, packed.reshape(-1))
+    return out.view((world,) + tuple(packed.shape))
+
+
 def gather_results(rois, count):
     """rois [B,post,5] f32, count [B] i32 of this rank -> ([world*B,post,5], [world*B]) in rank order.
-    Every rank must contribute the same B (pad the last shard with empty images if needed)."""
-    world = dist.get_world_size()
-    rois, count = rois.contiguous(), count.contiguous()
-    all_r = torch.empty((world * rois.shape[0],) + tuple(rois.shape[1:]), dtype=rois.dtype, device=rois.device)
-    all_c = torch.empty((world * count.shape[0],), dtype=count.dtype, device=count.device)
-    dist.all_gather_into_tensor(all_r, rois)
-    dist.all_gather_into_tensor(all_c, count)
+    Every rank must contribute the same B (pad the last shard with empty images if needed).  The counts ride in the
+    same buffer as the rois (bit patterns), so this is a single all-gather."""
+    B = rois.shape[0]
+    n = rois.numel()
+    packed = torch.cat([rois.reshape(-1), count.contiguous().view(torch.float32).reshape(-1)])
+    out = gather_packed(packed)
+    all_r = out[:, :n].reshape((out.shape[0] * B,) + tuple(rois.shape[1:]))
+    all_c = out[:, n:].contiguous().view(torch.int32).reshape(-1)
     return all_r, all_c

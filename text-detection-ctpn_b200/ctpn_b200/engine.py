@@ -115,9 +115,10 @@ class Engine:
         N.check(N.lib.ctpn_net_debug_tap(self._net, name.encode(), N.ptr(out), out.numel(), C.byref(cnt), N.stream_ptr()), "debug_tap")
         return out
 
-    def proposals(self, cls, bbox, im_info, cls_is_logit=True, cfg=None, ws_key="prop"):
+    def proposals(self, cls, bbox, im_info, cls_is_logit=True, cfg=None, ws_key="prop", out=None):
         """Batched proposal layer (proposal_layer_tf.py:14-157) on CUDA tensors.
-        Returns rois [B,post,5] (score,x1,y1,x2,y2), index [B,post] int32, count [B] int32."""
+        Returns rois [B,post,5] (score,x1,y1,x2,y2), index [B,post] int32, count [B] int32.
+        out=(rois, count): write into these (contiguous) tensors instead of allocating."""
         c = dict(self.cfg)
         if cfg:
             c.update(cfg)
@@ -128,9 +129,13 @@ class Engine:
         rows = post if post > 0 else max_n
         need = N.lib.ctpn_proposals_workspace_bytes(B, H, W, pre)
         ws = self._workspace(ws_key, need)
-        rois = torch.empty((B, rows, 5), dtype=torch.float32, device=self.device)
+        if out is not None:
+            rois, count = out
+            assert rois.shape == (B, rows, 5) and count.shape == (B,) and rois.is_contiguous() and count.is_contiguous()
+        else:
+            rois = torch.empty((B, rows, 5), dtype=torch.float32, device=self.device)
+            count = torch.empty((B,), dtype=torch.int32, device=self.device)
         index = torch.empty((B, rows), dtype=torch.int32, device=self.device)
-        count = torch.empty((B,), dtype=torch.int32, device=self.device)
         im_info = im_info.to(device=self.device, dtype=torch.float32).contiguous()
         N.check(N.lib.ctpn_proposals(N.ptr(cls.contiguous()), int(cls_is_logit), N.ptr(bbox.contiguous()), N.ptr(im_info),
                                      B, H, W, int(c["FEAT_STRIDE"]), pre, post, float(c["RPN_NMS_THRESH"]),
@@ -139,33 +144,53 @@ class Engine:
         return rois, index, count
 
     # ---- public API ------------------------------------------------------------------------
-    def detect_device(self, images, im_info):
+    def result_rows(self):
+        return int(self.cfg["RPN_POST_NMS_TOP_N"])
+
+    @staticmethod
+    def unpack(packed, B, rows):
+        """Views (rois [..,B,rows,5] f32, count [..,B] i32) of packed result buffers [.., B*rows*5 + B] (torch or numpy)."""
+        n = B * rows * 5
+        lead = tuple(packed.shape[:-1])
+        rois = packed[..., :n].reshape(lead + (B, rows, 5))
+        tail = packed[..., n:]
+        count = tail.view(torch.int32) if torch.is_tensor(tail) else tail.view(np.int32)
+        return rois, count
+
+    def detect_packed(self, images, im_info):
         """images: CUDA [B,H,W,3] uint8/float32; im_info: [B,3] tensor (blob_h, blob_w, scale).
-        Returns device tensors (rois [B,post,5], count [B])."""
-        n = min(self.streams, images.shape[0])
+        Returns ONE float32 device buffer [B*post*5 + B]: the rois of all images followed by the int32 counts
+        (bit pattern), so that the D2H / the multi-GPU gather of a batch's results is a single transfer."""
+        B = int(images.shape[0])
+        rows = self.result_rows()
+        packed = torch.empty(B * rows * 5 + B, dtype=torch.float32, device=self.device)
+        rois, count = self.unpack(packed, B, rows)
+        n = min(self.streams, B)
         if n <= 1:
             cls, bbox = self.forward_heads(images)
-            rois, _, count = self.proposals(cls, bbox, im_info, cls_is_logit=True)
-            return rois, count
+            self.proposals(cls, bbox, im_info, cls_is_logit=True, out=(rois, count))
+            return packed
         # sub-batches on side streams: the SIMT kernels of one sub-batch (conv1_1, BiLSTM, sort, NMS) run beside
         # the tensor-core kernels of the other (a persistent conv CTA leaves room for them on every SM)
         main = torch.cuda.current_stream()
         if len(self._side) < n:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(n)]
         im_info = im_info.to(self.device)
-        bounds = [images.shape[0] * i // n for i in range(n + 1)]
-        parts = []
+        bounds = [B * i // n for i in range(n + 1)]
         for i in range(n):
             st = self._side[i]
             st.wait_stream(main)
             with torch.cuda.stream(st):
-                sub = images[bounds[i]:bounds[i + 1]]
-                cls, bbox = self.forward_heads(sub, ws_key="net%d" % i)
-                r, _, c = self.proposals(cls, bbox, im_info[bounds[i]:bounds[i + 1]], cls_is_logit=True, ws_key="prop%d" % i)
-                parts.append((r, c))
+                lo, hi = bounds[i], bounds[i + 1]
+                cls, bbox = self.forward_heads(images[lo:hi], ws_key="net%d" % i)
+                self.proposals(cls, bbox, im_info[lo:hi], cls_is_logit=True, ws_key="prop%d" % i, out=(rois[lo:hi], count[lo:hi]))
         for st in self._side[:n]:
             main.wait_stream(st)
-        return torch.cat([r for r, _ in parts]), torch.cat([c for _, c in parts])
+        return packed
+
+    def detect_device(self, images, im_info):
+        """As detect_packed; returns device tensors (rois [B,post,5], count [B]) -- views of the packed buffer."""
+        return self.unpack(self.detect_packed(images, im_info), int(images.shape[0]), self.result_rows())
 
     def all_gather(self, rois, count):
         """Multi-GPU (one process per GPU, torch.distributed/NCCL initialised by the caller): every rank
@@ -173,6 +198,31 @@ class Engine:
         ordered by rank.  The only collective on the path (images are independent)."""
         from .dist import gather_results
         return gather_results(rois, count)
+
+    def _stage_host(self, images, slot=0):
+        """Host batch (ndarray / CPU tensor) -> pinned tensor.  A pinned tensor passes through; anything else is copied
+        into the pinned staging buffer of `slot` (callers that keep two transfers in flight alternate slots and wait
+        for the slot's previous H2D before calling)."""
+        if isinstance(images, torch.Tensor):
+            assert images.device.type == "cpu" and images.dtype in (torch.uint8, torch.float32)
+            src = images.contiguous()
+            if src.is_pinned():
+                return src
+            pinned = self._pin(("in", slot), tuple(src.shape), src.dtype)
+            pinned.copy_(src)
+            return pinned
+        arr = np.ascontiguousarray(images)
+        dt = torch.uint8 if arr.dtype == np.uint8 else torch.float32
+        pinned = self._pin(("in", slot), arr.shape, dt)
+        pinned.numpy()[...] = arr if dt == torch.uint8 else arr.astype(np.float32, copy=False)
+        return pinned
+
+    def _split_results(self, packed_h, B, rows):
+        """Pinned packed results [.., B*rows*5+B] -> list of per-image [n,5] arrays (rank order, image order)."""
+        rois, count = self.unpack(packed_h.numpy(), B, rows)
+        rois = rois.reshape(-1, rows, 5)
+        count = count.reshape(-1)
+        return [rois[i, :int(count[i])].copy() for i in range(rois.shape[0])]
 
     def rois_batch(self, images, im_info=None, gather=False):
         """images: host ndarray, (pinned) CPU tensor or device tensor [B,H,W,3] (uint8 BGR, or float32 mean-subtracted blob);
@@ -183,105 +233,106 @@ class Engine:
         if isinstance(images, torch.Tensor) and images.device.type == "cuda":
             # already resident (e.g. the output of resize_images): no staging, no H2D
             assert images.dtype in (torch.uint8, torch.float32)
-            B, H, W, _ = images.shape
             stage = images.contiguous()
-        elif isinstance(images, torch.Tensor):
-            # a pinned host tensor is transferred as is (no staging copy)
-            assert images.device.type == "cpu" and images.dtype in (torch.uint8, torch.float32)
-            B, H, W, _ = images.shape
-            stage = images.contiguous()
-            if not stage.is_pinned():
-                pinned = self._pin("in", tuple(stage.shape), stage.dtype)
-                pinned.copy_(stage)
-                stage = pinned
         else:
-            images = np.ascontiguousarray(images)
-            B, H, W, _ = images.shape
-            dt = torch.uint8 if images.dtype == np.uint8 else torch.float32
-            if dt == torch.float32:
-                images = images.astype(np.float32, copy=False)
-            stage = self._pin("in", images.shape, dt)
-            stage.numpy()[...] = images
+            stage = self._stage_host(images)
+        B, H, W, _ = stage.shape
         if im_info is None:
             im_info = np.array([[H, W, 1.0]] * B, np.float32)
         info_h = self._pin("info", (B, 3), torch.float32)
         info_h.numpy()[...] = np.asarray(im_info, np.float32).reshape(B, 3)
         dev = stage.to(self.device, non_blocking=True)
-        rois, count = self.detect_device(dev, info_h.to(self.device, non_blocking=True))
+        packed = self.detect_packed(dev, info_h.to(self.device, non_blocking=True))
         if gather:
-            rois, count = self.all_gather(rois, count)
-        rois_h = self._pin("rois", tuple(rois.shape), torch.float32)
-        cnt_h = self._pin("cnt", tuple(count.shape), torch.int32)
-        rois_h.copy_(rois, non_blocking=True)
-        cnt_h.copy_(count, non_blocking=True)
+            from .dist import gather_packed
+            packed = gather_packed(packed)
+        out_h = self._pin("out", tuple(packed.shape), torch.float32)
+        out_h.copy_(packed, non_blocking=True)       # one D2H: rois and counts travel together
         torch.cuda.current_stream().synchronize()
-        return [rois_h[b, :int(cnt_h[b])].numpy().copy() for b in range(rois_h.shape[0])]
+        return self._split_results(out_h, B, self.result_rows())
 
-    def rois_batches(self, batches, im_info=None):
-        """Pipelined version of rois_batch for a stream of equally shaped host batches (pinned uint8/float32
-        CPU tensors or ndarrays): the H2D copy of batch k+1 runs on a side stream while batch k is computed,
-        and results are read back with one small D2H per batch.  Yields the rois_batch() result of every batch
-        in order."""
-        copy_stream = getattr(self, "_copy_stream", None)
-        if copy_stream is None:
-            copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
+    def rois_batches(self, batches, im_info=None, gather=False):
+        """Pipelined version of rois_batch for a stream of equally shaped host batches (pinned uint8/float32 CPU tensors
+        or ndarrays).  Three stages overlap: the H2D copy of batch k+1 (copy stream), the compute of batch k (current
+        stream), and the multi-GPU gather (gather=True: one all-gather of the packed results) + D2H of batch k-1's
+        results (result stream).  The host blocks only on the event of the batch it is about to yield, after the next
+        batch's work has been enqueued, so the GPU never waits for Python.  Yields the rois_batch() result of every
+        batch in order."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._result_stream = torch.cuda.Stream(device=self.device)
+        copy_stream, result_stream = self._copy_stream, self._result_stream
         main = torch.cuda.current_stream()
-
+        rows = self.result_rows()
         bufs = self.__dict__.setdefault("_stream_bufs", {})   # two persistent device input buffers, used alternately
-        done = [None, None]  # event: compute that read buffer i has been enqueued and finished
+        computed = [None, None]    # event: the compute that read device buffer `slot` has finished
+        copied = [None, None]      # event: the H2D out of pinned staging buffer `slot` has finished
         counter = [0]
 
         def stage(images):
-            if isinstance(images, torch.Tensor):
-                src = images.contiguous()
-                if not src.is_pinned():
-                    pinned = self._pin("in", tuple(src.shape), src.dtype)
-                    pinned.copy_(src)
-                    src = pinned
-            else:
-                arr = np.ascontiguousarray(images)
-                dt = torch.uint8 if arr.dtype == np.uint8 else torch.float32
-                src = self._pin("in", arr.shape, dt)
-                src.numpy()[...] = arr if dt == torch.uint8 else arr.astype(np.float32, copy=False)
             slot = counter[0] & 1
             counter[0] += 1
+            if copied[slot] is not None:
+                copied[slot].synchronize()           # the staging buffer of this slot is free again (ADVICE r1: host race)
+            src = self._stage_host(images, slot)
             key = (slot, tuple(src.shape), src.dtype)
             if key not in bufs:
                 bufs[key] = torch.empty(tuple(src.shape), dtype=src.dtype, device=self.device)
             dev = bufs[key]
             with torch.cuda.stream(copy_stream):
-                if done[slot] is not None:
-                    copy_stream.wait_event(done[slot])     # the previous user of this buffer has finished
+                if computed[slot] is not None:
+                    copy_stream.wait_event(computed[slot])     # the previous user of this device buffer has finished
                 dev.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+            copied[slot] = ev
             return dev, ev, slot
+
+        def finish(pending):
+            out_h, ev, B, keep = pending
+            ev.synchronize()
+            del keep
+            return self._split_results(out_h, B, rows)
 
         it = iter(batches)
         try:
             nxt = stage(next(it))
         except StopIteration:
             return
+        pending = None
+        k = 0
         while nxt is not None:
             dev, ev, slot = nxt
-            try:
-                nxt = stage(next(it))          # overlaps with the compute enqueued below
-            except StopIteration:
-                nxt = None
             B, H, W, _ = dev.shape
             info = im_info if im_info is not None else np.array([[H, W, 1.0]] * B, np.float32)
-            info_h = self._pin("info", (B, 3), torch.float32)
+            info_h = self._pin(("info", k & 1), (B, 3), torch.float32)
             info_h.numpy()[...] = np.asarray(info, np.float32).reshape(B, 3)
             main.wait_event(ev)
-            rois, count = self.detect_device(dev, info_h.to(self.device, non_blocking=True))
-            done[slot] = torch.cuda.Event()
-            done[slot].record(main)
-            rois_h = self._pin("rois", tuple(rois.shape), torch.float32)
-            cnt_h = self._pin("cnt", tuple(count.shape), torch.int32)
-            rois_h.copy_(rois, non_blocking=True)
-            cnt_h.copy_(count, non_blocking=True)
-            main.synchronize()
-            yield [rois_h[b, :int(cnt_h[b])].numpy().copy() for b in range(rois_h.shape[0])]
+            packed = self.detect_packed(dev, info_h.to(self.device, non_blocking=True))
+            done = torch.cuda.Event()
+            done.record(main)
+            computed[slot] = done
+            with torch.cuda.stream(result_stream):
+                result_stream.wait_event(done)
+                res = packed
+                if gather:
+                    from .dist import gather_packed
+                    res = gather_packed(packed)
+                out_h = self._pin(("out", k & 1), tuple(res.shape), torch.float32)
+                out_h.copy_(res, non_blocking=True)
+                rev = torch.cuda.Event()
+                rev.record(result_stream)
+            this = (out_h, rev, B, (packed, res))
+            try:
+                nxt = stage(next(it))          # H2D of the next batch: overlaps the compute enqueued above
+            except StopIteration:
+                nxt = None
+            if pending is not None:
+                yield finish(pending)          # blocks on batch k-1 while batch k is already queued on the GPU
+            pending = this
+            k += 1
+        if pending is not None:
+            yield finish(pending)
 
     def detect_batch(self, images, im_scale=1.0):
         """Returns a list of (scores [n] f32, boxes [n,4] f32) per image, boxes divided by

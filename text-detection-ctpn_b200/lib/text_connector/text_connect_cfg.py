@@ -1,25 +1,23 @@
-"""Constants of the text-line stage, under the names the reference's callers use
-(lib/text_connector/text_connect_cfg.py; read as `Config.X` / `TextLineCfg.X`)."""
+"""Constants of the text-line stage under the names the reference's callers use
+(lib/text_connector/text_connect_cfg.py:2-12; read as `Config.X` / `TextLineCfg.X`, mutable class attributes)."""
 
-_IMAGE = dict(
-    SCALE=600,                     # resize_im: short side
-    MAX_SCALE=1200,                # resize_im: cap of the long side
-)
-_PROPOSALS = dict(
-    TEXT_PROPOSALS_WIDTH=16,       # anchor width (px)
-    TEXT_PROPOSALS_MIN_SCORE=0.7,  # proposals entering the connector
-    TEXT_PROPOSALS_NMS_THRESH=0.2,
-)
-_GRAPH = dict(
-    MAX_HORIZONTAL_GAP=50,         # px searched to the left / right for a neighbour
-    MIN_V_OVERLAPS=0.7,            # vertical overlap of neighbours
-    MIN_SIZE_SIM=0.7,              # height similarity of neighbours
-)
-_LINES = dict(
-    MIN_NUM_PROPOSALS=2,
-    MIN_RATIO=0.5,                 # width / height of a kept line
-    LINE_MIN_SCORE=0.9,
-)
 
-Config = type("Config", (), {**_IMAGE, **_PROPOSALS, **_GRAPH, **_LINES,
-                             "__doc__": "Text-line construction constants (mutable class attributes, as in the reference)."})
+class Config:
+    SCALE = 600
+    MAX_SCALE = 1200
+    TEXT_PROPOSALS_WIDTH = 16
+    MIN_NUM_PROPOSALS = 2
+    MIN_RATIO = 0.5
+    LINE_MIN_SCORE = 0.9
+    MAX_HORIZONTAL_GAP = 50
+    TEXT_PROPOSALS_MIN_SCORE = 0.7
+    TEXT_PROPOSALS_NMS_THRESH = 0.2
+    MIN_V_OVERLAPS = 0.7
+    MIN_SIZE_SIM = 0.7
+
+
+def native_cfg():
+    """The constants in the order ctpn_text_*_host take them (include/ctpn_b200.h), read at call time."""
+    c = Config
+    return (c.TEXT_PROPOSALS_MIN_SCORE, c.TEXT_PROPOSALS_NMS_THRESH, c.MAX_HORIZONTAL_GAP, c.MIN_V_OVERLAPS, c.MIN_SIZE_SIM,
+            c.MIN_RATIO, c.LINE_MIN_SCORE, c.TEXT_PROPOSALS_WIDTH, c.MIN_NUM_PROPOSALS)

@@ -37,6 +37,19 @@ def e4m3(t):
     return (t * s).to(torch.float32).to(torch.float8_e4m3fn).to(t.dtype) / s
 
 
+def f16(t):
+    return t.to(torch.float16).to(t.dtype)
+
+
+def e4m3_head(t, headroom=3):
+    """e4m3 with a static-style scale: the tensor's max lands `headroom` binades below 448 (calibrated scale + margin)."""
+    m = float(t.abs().max())
+    if m == 0.0:
+        return t
+    s = 2.0 ** (np.floor(np.log2(448.0 / m)) - headroom)
+    return (t * s).to(torch.float32).to(torch.float8_e4m3fn).to(t.dtype) / s
+
+
 def conv_stack(blob, weights, mode, acc=torch.float64):
     x = torch.from_numpy(np.ascontiguousarray(blob)).to(acc).permute(0, 3, 1, 2)
     for name, cin, cout, pool in net_cpu.CONV_LAYERS:
@@ -44,6 +57,16 @@ def conv_stack(blob, weights, mode, acc=torch.float64):
         b = torch.from_numpy(weights[name + "/biases"]).to(acc)
         if mode == "exact":
             y = F.conv2d(x, w, b, padding=1)
+        elif mode.startswith("f16"):
+            # fp16 hi planes (11 significant bits, residual 2^-12) + e4m3 cross terms: 1 + 2 * 1/2 = 2 units
+            a0 = f16(x.float()).to(acc)
+            w0 = f16(w.float()).to(acc)
+            y = F.conv2d(a0, w0, b, padding=1)
+            if mode != "f16x1":
+                a1 = (x - a0).float().to(acc)
+                w1 = (w - w0).float().to(acc)
+                q = {"f16f8": e4m3, "f16f8h": e4m3_head, "f16x2": lambda t: f16(t.float()).to(acc)}[mode]
+                y = y + F.conv2d(q(a0), q(w1), None, padding=1) + F.conv2d(q(a1), q(w0), None, padding=1)
         else:
             a0 = bf16(x.float()).to(acc)
             w0 = bf16(w.float()).to(acc)
@@ -75,6 +98,7 @@ def main():
     ap.add_argument("--height", type=int, default=600)
     ap.add_argument("--width", type=int, default=900)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--modes", default="bf16x1,bf16x2,fp8cross,f16x1,f16f8,f16f8h,f16x2")
     a = ap.parse_args()
     torch.set_num_threads(min(32, os.cpu_count() or 1))
     w = synth.make_weights(0)
@@ -84,7 +108,7 @@ def main():
         ref_feat = conv_stack(blob, w, "exact")
         ref = heads(ref_feat, w)
         print("reference: |cls| max %.3f  |bbox| max %.3f  feature max %.3f" % (np.abs(ref[0]).max(), np.abs(ref[1]).max(), float(ref_feat.max())))
-        for mode in ("bf16x1", "bf16x2", "fp8cross"):
+        for mode in a.modes.split(","):
             feat = conv_stack(blob, w, mode)
             got = heads(feat, w)
             fe = float((feat - ref_feat).abs().max() / ref_feat.abs().max())
