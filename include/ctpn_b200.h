@@ -13,7 +13,7 @@
  *                        (called by lib/utils/gpu_nms.pyx:31)
  *   ctpn_nms_sorted      lib/utils/nms_kernel.cu:34-78 (nms_kernel) + :124-139 (host greedy scan)
  *   ctpn_proposals       lib/rpn_msr/proposal_layer_tf.py:14-157 (tf.py_func body, lib/networks/network.py:214)
- *   ctpn_conv1_1_tc / ctpn_conv1_1 / ctpn_conv3x3 (taps=9, optional fused 2x2 max-pool)
+ *   ctpn_conv1_1_tc / ctpn_conv3x3 (taps=9, optional fused 2x2 max-pool)
  *                        lib/networks/network.py:160-183 (conv), :189-196 (max_pool)
  *   ctpn_bilstm_recurrent, ctpn_conv3x3 (taps=1: x-projection, FC and head matmuls)
  *                        lib/networks/network.py:88-113 (Bilstm), :144-158 (lstm_fc)
@@ -92,14 +92,10 @@ int ctpn_proposals(const float *cls, int cls_is_logit, const float *bbox, const 
 int ctpn_pack_weights(const float *w_tf, int taps, int cin, int cout, int cout_pad, int planes,
                       void *w_planes_out, void *stream);
 
-/* conv1_1: uint8 BGR image [B][H][W][3] (or float32 blob when src_is_f32) -> 64-channel planes,
- * float32 direct convolution; fuses the mean subtraction of lib/fast_rcnn/test.py:9
- * (lut[256][3] = float32(double(v) - PIXEL_MEANS[c])), bias and ReLU. */
-int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, const float *w_hwio,
-                 const float *bias, void *out_planes, int B, int H, int W, int planes, void *stream);
-
-/* Same layer on the tensor cores: the im2col tile (K = 27 padded to 32) is built in shared memory as bf16
- * planes and multiplied by the resident weight tile with tcgen05.mma; HBM-write bound.  Default in ctpn_net_forward. */
+/* conv1_1: uint8 BGR image [B][H][W][3] (or float32 blob when src_is_f32) -> 64-channel planes; fuses the mean
+ * subtraction of lib/fast_rcnn/test.py:9 (lut[256][3] = float32(double(v) - PIXEL_MEANS[c])), bias and ReLU.  On the
+ * tensor cores: the im2col tile (K = 27 padded to 32) is built in shared memory as bf16 planes and multiplied by the
+ * resident weight tile with tcgen05.mma; HBM-write bound. */
 int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const float *w_hwio,
                     const float *bias, void *out_planes, int B, int H, int W, int planes, void *stream);
 
@@ -111,12 +107,6 @@ int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const flo
 #define CTPN_F_OUT_F32 4
 int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B,
                  int H, int W, int cin, int cout, int taps, int planes, int flags, void *stream);
-/* Same contract, float32 SIMT implementation (no tensor cores): kernel-level reference used
- * by the tests and by CTPN_CONV_IMPL=simt. */
-int ctpn_conv3x3_simt(const void *in_planes, const void *w_planes, const float *bias, void *out,
-                      int B, int H, int W, int cin, int cout, int taps, int planes, int flags,
-                      void *stream);
-
 /* BiLSTM recurrence (network.py:97-101).  xproj: float32 [R][W][1024] = x.Wx + b for
  * (fw gates i,j,f,o | bw gates i,j,f,o); wh_fw / wh_bw: float32 [128][512] recurrent kernels
  * (rows 512..639 of the TF kernel).  Output planes [P][R][W][256] = concat(h_fw, h_bw). */
@@ -128,8 +118,7 @@ typedef struct ctpn_net ctpn_net_t;
 int ctpn_net_create(ctpn_net_t **net, int planes);
 int ctpn_net_destroy(ctpn_net_t *net);
 /* options: "keep_activations" (1: every layer gets its own workspace region so that
- * ctpn_net_debug_tap can read all of them after a forward), "conv_simt" (1: run the float32 SIMT
- * reference kernels instead of the tcgen05 path), "conv1_simt" (1: float32 SIMT conv1_1 only). */
+ * ctpn_net_debug_tap can read all of them after a forward). */
 int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value);
 /* name = TF variable name; data = host float32 in TF layout. */
 int ctpn_net_set_weight(ctpn_net_t *net, const char *name, const float *data_host, size_t count);
@@ -176,22 +165,6 @@ int ctpn_text_filter_nms_host(const float *proposals, const float *scores, int n
                               int *num_keep);
 int ctpn_text_groups_host(const float *proposals, const float *scores, int m, int im_w, const float *cfg9, int *offsets,
                           int *members, int members_capacity, int *num_groups, int *num_members);
-
-/* ---- diagnostics (not on the product path) ----------------------------------------------
- * Hardware probe used by tests/probe_umma_view.py: reads a [rows][64] bf16 matrix through a UMMA
- * K-major SWIZZLE_128B descriptor that starts at row `row0` with `group_stride_rows` between 8-row
- * groups, against the identity, and returns the 128x64 values the tensor core fetched. */
-int ctpn_probe_umma_view(const void *a_bf16, const void *identity_bf16, int rows, int row0,
-                         int group_stride_rows, int base_offset_mode, float *out, void *stream);
-
-/* Hardware probe: every CTA issues n_mma 128 x bn x 16 bf16 MMAs with a tcgen05.commit every
- * `commit_every` MMAs and (lag > 0) waits on each commit `lag` commits later.  Timed by the caller. */
-int ctpn_probe_mma_rate(int bn, int n_mma, int commit_every, int lag, int alternate_acc, int fence_each,
-                        int grid, void *stream);
-
-/* Hardware probe: the same back-to-back issue loop with cta_group::2 instructions (M = 256 over a 2-CTA cluster,
- * each CTA holding its 128 A rows and bn/2 rows of B).  grid must be even; n_mma a multiple of 8. */
-int ctpn_probe_mma_rate_pair(int bn, int n_mma, int alternate_acc, int grid, void *stream);
 
 #ifdef __cplusplus
 }

@@ -146,6 +146,43 @@ def cmd_bilstm(a):
     return 0 if ok else 1
 
 
+def cmd_net_simt(a):
+    """Whole network, tcgen05 kernels vs the float32 SIMT reference kernels of the test library (same planes)."""
+    import torch
+    from ctpn_b200 import Engine
+    from oracle import synth
+    w = synth.make_weights(0)
+    ims = np.stack([synth.make_image(20 + i, a.H, a.W) for i in range(a.B)])
+    x = torch.from_numpy(ims).cuda()
+    c1, b1 = Engine(w, planes=a.planes).forward_heads(x)
+    c2, b2 = Engine(w, planes=a.planes, conv_simt=True).forward_heads(x)
+    d = max(float((c1 - c2).abs().max()), float((b1 - b2).abs().max()))
+    ok = d < a.tol
+    print(json.dumps(dict(ok=bool(ok), head_diff=d, tol=a.tol)))
+    return 0 if ok else 1
+
+
+def cmd_proposals_generic(a):
+    """CTPN_GENERIC_NMS=1 (test library): every image through the generic bitmask NMS; equals the oracle exactly."""
+    import torch
+    from ctpn_b200.engine import Engine
+    from oracle import postproc, synth
+    assert os.environ.get("CTPN_GENERIC_NMS") and os.environ.get("CTPN_B200_LIB") == "dbg"
+    eng = Engine(None)
+    H, W = 12, 18
+    cls = np.concatenate([synth.make_head_outputs(200 + s, H, W)[0] for s in range(2)])
+    box = np.concatenate([synth.make_head_outputs(200 + s, H, W)[1] for s in range(2)])
+    info = np.array([[192, 100, 1.0], [192, 288, 1.0]], np.float32)
+    rois, index, count = eng.proposals(torch.from_numpy(cls).cuda(), torch.from_numpy(box).cuda(), torch.from_numpy(info), cls_is_logit=False)
+    ok = True
+    for b in range(2):
+        want, _, idx = postproc.proposal_layer(cls[b:b + 1], box[b:b + 1], info[b:b + 1], return_index=True)
+        n = int(count[b])
+        ok = ok and n == want.shape[0] and np.array_equal(index[b, :n].cpu().numpy(), idx) and np.array_equal(rois[b, :n].cpu().numpy(), want)
+    print(json.dumps(dict(ok=bool(ok))))
+    return 0 if ok else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -160,8 +197,14 @@ def main():
     l = sub.add_parser("bilstm")
     for k, d in dict(R=37, W=56, planes=2, seed=0).items():
         l.add_argument("--" + k, type=int, default=d)
+    ns = sub.add_parser("net_simt")
+    for k, d in dict(B=3, H=128, W=192, planes=2).items():
+        ns.add_argument("--" + k, type=int, default=d)
+    ns.add_argument("--tol", type=float, default=5e-4)
+    sub.add_parser("proposals_generic")
     a = ap.parse_args()
-    return {"conv": cmd_conv, "conv1": cmd_conv1, "bilstm": cmd_bilstm}[a.cmd](a)
+    return {"conv": cmd_conv, "conv1": cmd_conv1, "bilstm": cmd_bilstm, "net_simt": cmd_net_simt,
+            "proposals_generic": cmd_proposals_generic}[a.cmd](a)
 
 
 if __name__ == "__main__":

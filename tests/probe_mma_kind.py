@@ -6,10 +6,9 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "text-detection-ctpn_b200"))
+os.environ["CTPN_B200_LIB"] = "dbg"      # the probes live in the test library
 from ctpn_b200 import _native as N  # noqa: E402
 fn = N.lib.ctpn_probe_mma_kind
-fn.restype = C.c_int
-fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 torch.cuda.set_device(0)
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 n = 48000

@@ -4,6 +4,7 @@ import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "text-detection-ctpn_b200"))
+os.environ["CTPN_B200_LIB"] = "dbg"      # the probes live in the test library
 from ctpn_b200 import _native as N  # noqa: E402
 torch.cuda.set_device(0)
 sms = torch.cuda.get_device_properties(0).multi_processor_count

@@ -11,6 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "text-detection-ctpn_b200"))
+os.environ["CTPN_B200_LIB"] = "dbg"      # the probes live in the test library
 from ctpn_b200 import _native as N  # noqa: E402
 
 dev = torch.device("cuda", 0)

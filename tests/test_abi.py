@@ -25,6 +25,22 @@ def test_ctypes_table_matches_header():
     assert sorted(N.SIGNATURES) == header_functions()
 
 
+def test_product_library_has_no_test_only_symbols_and_debug_library_has_them():
+    """Probes, SIMT reference kernels and ablation switches live in tests/_native/libctpn_b200_dbg.so
+    (csrc/testing/ctpn_b200_testing.h), not in the shipped library or the public header."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "text-detection-ctpn_b200", "csrc", "testing", "ctpn_b200_testing.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    test_only = sorted(set(re.findall(r"\b(ctpn_[a-z0-9_]+)\s*\(", hdr)))
+    assert sorted(N.TESTING_SIGNATURES) == test_only and len(test_only) >= 6
+    dbg = C.CDLL(os.path.join(ROOT, "tests", "_native", "libctpn_b200_dbg.so"))
+    for n in test_only:
+        assert not hasattr(N.lib, n), "product library exports test-only symbol %s" % n
+        assert hasattr(dbg, n)
+    for n in header_functions():
+        assert hasattr(dbg, n)
+
+
 def test_version_and_error_string():
     assert N.lib.ctpn_version() >= 100
     assert isinstance(N.last_error(), str)

@@ -14,6 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 RELU, POOL, F32 = 1, 2, 4
 
 
+DBG = {"CTPN_B200_LIB": "dbg"}     # tests/_native/libctpn_b200_dbg.so: SIMT references, tuning / ablation switches
+
+
 def run_check(*args, timeout=300, env=None):
     cmd = [sys.executable, os.path.join(HERE, "gpu_checks.py")] + [str(a) for a in args]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
@@ -54,8 +57,8 @@ def test_conv_tcgen05(case):
 
 @pytest.mark.parametrize("case", [TC_CASES[4], TC_CASES[5], TC_CASES[7]], ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
 def test_conv_tcgen05_single_cta_variant(case):
-    """3x3 layers default to 2-CTA clusters with multicast weight tiles; CTPN_TC_MCAST=0 is the one-CTA-per-tile variant."""
-    run_check(*conv_args(*case), env={"CTPN_TC_MCAST": "0"})
+    """3x3 layers default to 2-CTA clusters with multicast weight tiles; CTPN_TC_MCAST=0 (test library) is the one-CTA-per-tile variant."""
+    run_check(*conv_args(*case), env=dict(DBG, CTPN_TC_MCAST="0"))
 
 
 SIMT_CASES = [
@@ -67,7 +70,7 @@ SIMT_CASES = [
 
 @pytest.mark.parametrize("case", SIMT_CASES, ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_p%d_f%d" % c)
 def test_conv_simt_reference(case):
-    run_check(*conv_args(*case, impl="simt"))
+    run_check(*conv_args(*case, impl="simt"), env=DBG)
 
 
 @pytest.mark.parametrize("R,W,planes", [(37, 56, 2), (5, 7, 3), (1184, 56, 1), (600, 100, 2)])
@@ -78,4 +81,4 @@ def test_bilstm_recurrence(R, W, planes):
 @pytest.mark.parametrize("B,H,W,planes,impl", [(2, 37, 45, 2, "tc"), (1, 16, 8, 1, "tc"), (1, 50, 70, 3, "tc"), (1, 600, 900, 2, "tc"),
                                                (2, 37, 45, 2, "simt"), (1, 50, 70, 3, "simt")])
 def test_conv1_1(B, H, W, planes, impl):
-    run_check("conv1", "--B", B, "--H", H, "--W", W, "--planes", planes, "--impl", impl)
+    run_check("conv1", "--B", B, "--H", H, "--W", W, "--planes", planes, "--impl", impl, env=DBG if impl == "simt" else None)

@@ -83,13 +83,16 @@ def test_cfgB_sized_and_logit_input():
     assert got[:, 1:].min() >= 0 and got[:, [1, 3]].max() <= 1599 and got[:, [2, 4]].max() <= 1199
 
 
-@pytest.mark.parametrize("force_generic", [False, True])
-def test_unstructured_boxes_take_the_generic_nms_path(force_generic):
+def test_generic_nms_forced_for_every_image():
+    """CTPN_GENERIC_NMS=1 (a switch of the test library only) disables the column path altogether."""
+    from test_conv_gpu import DBG, run_check
+    run_check("proposals_generic", env=dict(DBG, CTPN_GENERIC_NMS="1"))
+
+
+def test_unstructured_boxes_take_the_generic_nms_path():
     """im_info narrower than the feature map: boxes of many columns are clipped onto the same x range, so
     the column decomposition does not hold.  The device detects it per image and falls back to the generic
-    bitmask NMS; results still equal the oracle exactly.  Image 1 of the batch is a normal (structured) one.
-    With CTPN_GENERIC_NMS=1 the column path is disabled altogether (both images through the generic path)."""
-    import os
+    bitmask NMS; results still equal the oracle exactly.  Image 1 of the batch is a normal (structured) one."""
     import torch
     from ctpn_b200.engine import Engine
     eng = Engine(None)
@@ -97,12 +100,7 @@ def test_unstructured_boxes_take_the_generic_nms_path(force_generic):
     cls = np.concatenate([synth.make_head_outputs(200 + s, H, W)[0] for s in range(2)])
     box = np.concatenate([synth.make_head_outputs(200 + s, H, W)[1] for s in range(2)])
     info = np.array([[192, 100, 1.0], [192, 288, 1.0]], np.float32)
-    if force_generic:
-        os.environ["CTPN_GENERIC_NMS"] = "1"
-    try:
-        rois, index, count = eng.proposals(torch.from_numpy(cls).cuda(), torch.from_numpy(box).cuda(), torch.from_numpy(info), cls_is_logit=False)
-    finally:
-        os.environ.pop("CTPN_GENERIC_NMS", None)
+    rois, index, count = eng.proposals(torch.from_numpy(cls).cuda(), torch.from_numpy(box).cuda(), torch.from_numpy(info), cls_is_logit=False)
     for b in range(2):
         want, _, idx = postproc.proposal_layer(cls[b:b + 1], box[b:b + 1], info[b:b + 1], return_index=True)
         n = int(count[b])

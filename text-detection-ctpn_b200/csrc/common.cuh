@@ -36,6 +36,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 
 // Optional per-launch timing: when enabled through ctpn_prof_enable(1), every instrumented launch is
 // bracketed by CUDA events on its own stream; `work` is the algorithmic FLOPs (or bytes) of the launch.
+bool prof_enabled();
 struct ProfScope {
   ProfScope(const char *label, double work, cudaStream_t st);
   ~ProfScope();

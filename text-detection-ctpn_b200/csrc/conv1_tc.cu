@@ -15,10 +15,19 @@
 // stage per group the builder sat idle for the arrive -> MMA -> commit round trip (~1000 cycles) on every tile.
 // Numerics: operands carry P bf16 planes like every other tensor-core layer (planes=3 is float32-equivalent).
 // Reference semantics: lib/networks/network.py:160-183 (conv1_1), lib/fast_rcnn/test.py:8-9 (mean subtraction).
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace ctpn {
+
+#ifdef CTPN_DEBUG
+#define C1_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define C1_DBG(p, bit) false
+#endif
+
 
 constexpr int kC1tThreads = 544;          // warp 0: MMA issuer / TMEM owner, warps 1-8: two builder groups, warps 9-16: epilogue
 constexpr int kC1tTileBytes = 128 * 128;  // one plane of the A tile (128 pixels x 128-byte rows)
@@ -31,7 +40,7 @@ struct Conv1TcParams {
   __nv_bfloat16 *out;
   int B, H, W, src_is_f32;
   int tiles_x, tiles_y, total_tiles;
-  int debug;   // CTPN_C1_DEBUG bits (perf experiments only): 1 skip patch staging, 2 skip tile build, 4 skip stores, 8 skip epilogue math
+  int debug;   // test library only (CTPN_C1_DEBUG bits): 1 skip patch staging, 2 skip tile build, 4 skip stores, 8 skip epilogue math
   long long plane_stride;
 };
 
@@ -158,7 +167,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
         const int i = m + u * 128;
         const int xx = i % 10, yy = i / 10;
         const int gx = x0 + xx - 1, gy = y0 + yy - 1;
-        if (i < 180 && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && !(p.debug & 1)) {
+        if (i < 180 && gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && !C1_DBG(p, 1)) {
           const size_t off = (((size_t)b * p.H + gy) * p.W + gx) * 3;
           if (p.src_is_f32) {
             const float *q = reinterpret_cast<const float *>(p.src) + off;
@@ -204,7 +213,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
       else asm volatile("bar.sync 2, 128;" ::: "memory");
       uint8_t *arow = base + s * P * kC1tTileBytes + m * 128;
 #pragma unroll
-      for (int chunk = 0; chunk < ((p.debug & 2) ? 0 : 4); ++chunk) {
+      for (int chunk = 0; chunk < (C1_DBG(p, 2) ? 0 : 4); ++chunk) {
         uint32_t pk[3][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -249,7 +258,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
       mbar_wait(tfull + 8 * a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
-      if (!(p.debug & 8)) {
+      if (!C1_DBG(p, 8)) {
         const int chunk = (warp - 9) >> 2;
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
@@ -285,7 +294,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
           for (int it = 0; it < 4; ++it) {
             const int pp = it * 8 + (lane >> 2);
             const uint4 val = stage_w[pp * 4 + ((lane & 3) ^ ((pp >> 1) & 3))];
-            if (((okmask >> pp) & 1u) && !(p.debug & 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
+            if (((okmask >> pp) & 1u) && !C1_DBG(p, 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
           }
         }
       }
@@ -307,10 +316,21 @@ template <int P>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)(P <= 2 ? 4 : 2) * P * kC1tTileBytes + (size_t)P * 64 * 128 + (4 * kC1tPatch + 768) * sizeof(float) +
                       8 * 32 * kC1tStagePitch + 96 + 16;
-  CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0;
+  constexpr int kMaxDevices = 64;
+  static std::mutex mu;
+  static int sm_count[kMaxDevices];      // per device: SM count (0 = attribute not set yet)
+  int dev = 0;
   CTPN_CUDA(cudaGetDevice(&dev));
-  CTPN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CTPN_REQUIRE(dev >= 0 && dev < kMaxDevices, "ctpn_conv1_1_tc: device index %d not supported", dev);
+  int sms;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (sm_count[dev] == 0) {
+      CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CTPN_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    }
+    sms = sm_count[dev];
+  }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   ProfScope prof("conv1_1", 2.0 * p.B * p.H * p.W * 27.0 * 64.0, st);
   conv1_tc_kernel<P><<<grid, kC1tThreads, smem, st>>>(p);
@@ -336,10 +356,12 @@ extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut
   CTPN_REQUIRE(total < (1ll << 31), "ctpn_conv1_1_tc: too many tiles");
   p.total_tiles = (int)total;
   p.plane_stride = (long long)B * H * W * 64;
-  {
-    const char *e = getenv("CTPN_C1_DEBUG");
-    p.debug = e ? atoi(e) : 0;
-  }
+#ifdef CTPN_DEBUG
+  static const int dbg = [] { const char *e = getenv("CTPN_C1_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
+#else
+  p.debug = 0;
+#endif
   cudaStream_t st = (cudaStream_t)stream;
   if (planes == 1) return launch_conv1_tc<1>(p, st);
   if (planes == 2) return launch_conv1_tc<2>(p, st);

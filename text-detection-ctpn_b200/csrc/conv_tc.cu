@@ -26,12 +26,22 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
 
 namespace ctpn {
+
+// Ablation switches (skip loads / MMAs / stores) exist only in the test library (-DCTPN_DEBUG, env CTPN_TC_DEBUG); in
+// the product build the tests below are compile-time false and the branches disappear.
+#ifdef CTPN_DEBUG
+#define CTPN_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define CTPN_DBG(p, bit) false
+#endif
 
 struct ConvTcParams {
   int B, H, W, Cin, Cout, taps, planes, flags;
@@ -45,7 +55,7 @@ struct ConvTcParams {
   int cout_pad;
   int Ho, Wo;
   int stages_a, stages_b;
-  int debug;                // CTPN_TC_DEBUG bits (perf experiments only): 1 skip B loads, 2 skip A loads, 4 skip MMAs, 8 skip stores
+  int debug;                // test library only (CTPN_TC_DEBUG bits): 1 skip B loads, 2 skip A loads, 4 skip MMAs, 8 skip stores
   int nbuf;                 // TMEM tile buffers: 2 = epilogue overlaps the next tile's MMAs, 1 = serialised
   const float *bias;
   void *out;
@@ -147,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(emptyA + 8 * s, ph ^ 1u);
           if (elect_one()) {
-            if (p.debug & 2) { mbar_arrive(fullA + 8 * s); }
+            if (CTPN_DBG(p, 2)) { mbar_arrive(fullA + 8 * s); }
             else {
               mbar_arrive_expect_tx(fullA + 8 * s, (uint32_t)P * (uint32_t)p.patch_tx_bytes);
               for (int pl = 0; pl < P; ++pl)
@@ -171,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int tap = 0; tap < TAPS; ++tap) {
             mbar_wait(emptyB + 8 * s, ph ^ 1u);
             if (elect_one()) {
-              if (p.debug & 1) { mbar_arrive(fullB + 8 * s); }
+              if (CTPN_DBG(p, 1)) { mbar_arrive(fullB + 8 * s); }
               else {
                 mbar_arrive_expect_tx(fullB + 8 * s, b_stage);   // MC: own half + the peer's multicast half
                 for (int pl = 0; pl < P; ++pl) {
@@ -216,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             constexpr int kPW = 10;
             const uint32_t view16 = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + tap % 3) * 8u : 0u;
             const uint32_t not_first = (kb | tap) != 0;
-            if (elect_one() && !(p.debug & 4)) {
+            if (elect_one() && !CTPN_DBG(p, 4)) {
 #pragma unroll
               for (int i = 0; i < P; ++i) {
 #pragma unroll
@@ -290,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
 #pragma unroll 1
-      for (int chunk = eset; chunk < ((p.debug & 16) ? 0 : BN / 32); chunk += 2) {
+      for (int chunk = eset; chunk < (CTPN_DBG(p, 16) ? 0 : BN / 32); chunk += 2) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
         tmem_ld_wait();
@@ -340,7 +350,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w[pl][4 * q], w[pl][4 * q + 1], w[pl][4 * q + 2], w[pl][4 * q + 3]);
             __syncwarp();
-            if (c0 < p.Cout && !(p.debug & 8)) {
+            if (c0 < p.Cout && !CTPN_DBG(p, 8)) {
               __nv_bfloat16 *obase = reinterpret_cast<__nv_bfloat16 *>(p.out) + (long long)pl * p.out_plane_stride + c0 + (lane & 3) * 8;
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
@@ -350,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-        } else if (ok && c0 < p.Cout && !(p.debug & 8)) {
+        } else if (ok && c0 < p.Cout && !CTPN_DBG(p, 8)) {
           if (out_f32) {
             float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.out) + pix * p.Cout + c0);
 #pragma unroll
@@ -374,15 +384,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ---- host side -------------------------------------------------------------------------------
-static int g_num_sms = 0;
+// Per-device launch state: SM count, the dynamic-shared-memory attribute and the co-resident cluster count of every
+// kernel instantiation (set once per device, under a mutex), and a small cache of encoded tensor maps keyed by the
+// tensor they describe, so that a steady-state ctpn_conv3x3 call does no driver work besides the launch itself.
+constexpr int kMaxDevices = 64;
+static std::mutex g_mu;
+static int g_sms[kMaxDevices];
 
-static int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
+struct Tuning { int debug = 0, bn = 0, stages_a = 0, stages_b = 0, mcast = 1; };
+static const Tuning &tuning() {            // read once at first use; overrides exist only in the test library
+  static const Tuning t = [] {
+    Tuning v;
+#ifdef CTPN_DEBUG
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    v.debug = env_int("CTPN_TC_DEBUG", 0);
+    v.bn = env_int("CTPN_TC_BN", 0);
+    v.stages_a = env_int("CTPN_TC_STAGES_A", 0);
+    v.stages_b = env_int("CTPN_TC_STAGES_B", 0);
+    v.mcast = env_int("CTPN_TC_MCAST", 1);
+#endif
+    return v;
+  }();
+  return t;
+}
+
+struct TmapKey {
+  const void *ptr;
+  unsigned long long d0, d1, d2, d3;
+  unsigned b0, b1, b2, b3;
+  int dev;
+  bool operator==(const TmapKey &o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 &&
+           b3 == o.b3 && dev == o.dev;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey &k) const {
+    size_t h = std::hash<const void *>()(k.ptr);
+    for (unsigned long long v : {k.d0, k.d1, k.d2, k.d3, (unsigned long long)k.b0, (unsigned long long)k.b1,
+                                 (unsigned long long)k.b2, (unsigned long long)k.b3, (unsigned long long)k.dev})
+      h = h * 1000003u ^ std::hash<unsigned long long>()(v);
+    return h;
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+
+// bf16 tensor map (128-B swizzle) of `rank` dimensions, from the cache or freshly encoded
+static int cached_tmap(int dev, CUtensorMap *out, const void *ptr, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                       const cuuint32_t *box) {
+  TmapKey k{ptr, dims[0], dims[1], rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0], box[1], rank > 2 ? box[2] : 0,
+            rank > 3 ? box[3] : 0, dev};
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_tmaps.find(k);
+  if (it != g_tmaps.end()) { *out = it->second; return CTPN_OK; }
+  EncodeTiledFn enc = nullptr;
+  int rc = tma_get_encode(&enc);
+  if (rc) return rc;
+  if ((rc = tma_encode_bf16(enc, out, const_cast<void *>(ptr), rank, dims, strides, box))) return rc;
+  if (g_tmaps.size() >= 1024) g_tmaps.clear();      // bounded: callers cycle through a handful of buffers
+  g_tmaps.emplace(k, *out);
+  return CTPN_OK;
 }
 
 template <int BN, int P, int TAPS, int MC>
-static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
+static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
   const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
   const size_t budget = 227 * 1024 - 1024 - kCtrlBytes - kStageBytes;
   // activation ring: two stages when they leave room for at least two weight stages, else one
@@ -391,40 +456,43 @@ static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams 
   CTPN_REQUIRE(sa * a_stage + b_stage <= budget, "conv_tc: pipeline stages (%zu + %zu B) do not fit in shared memory", a_stage, b_stage);
   int sb = (int)((budget - sa * a_stage) / b_stage);
   if (sb > kMaxStages) sb = kMaxStages;
-  sa = std::max(1, std::min(sa, env_int("CTPN_TC_STAGES_A", sa)));
-  sb = std::max(1, std::min(sb, env_int("CTPN_TC_STAGES_B", sb)));
+  if (tuning().stages_a > 0) sa = std::max(1, std::min(sa, tuning().stages_a));
+  if (tuning().stages_b > 0) sb = std::max(1, std::min(sb, tuning().stages_b));
   p.stages_a = sa;
   p.stages_b = sb;
-  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kStageBytes + kCtrlBytes;
+  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kStageBytes + kCtrlBytes;   // a constant of the instantiation
   auto kernel = conv_tc_kernel<BN, P, TAPS, MC>;
-  CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  char label[128];
-  snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d p%d bn%d%s", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, p.planes, BN, MC ? " mc" : "");
-  ProfScope prof(label, 2.0 * p.B * p.H * p.W * (double)p.taps * p.Cin * p.Cout, st);
-  if (MC) {
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    static int max_clusters = 0;      // co-resident 2-CTA clusters of this instantiation (one CTA per SM)
-    if (max_clusters == 0) {
-      cfg.gridDim = dim3(2 * (g_num_sms / 2));
-      int n = 0;
-      CTPN_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
-      CTPN_REQUIRE(n > 0, "conv_tc: no 2-CTA cluster of this kernel fits on the device");
-      max_clusters = n;
+  static bool attr_set[kMaxDevices];
+  static int max_clusters[kMaxDevices];     // co-resident 2-CTA clusters of this instantiation (one CTA per SM)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = &attr;
+  cfg.numAttrs = MC ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!attr_set[dev]) {
+      CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (MC) {
+        cfg.gridDim = dim3(2 * (g_sms[dev] / 2));
+        int n = 0;
+        CTPN_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+        CTPN_REQUIRE(n > 0, "conv_tc: no 2-CTA cluster of this kernel fits on the device");
+        max_clusters[dev] = n;
+      }
+      attr_set[dev] = true;
     }
-    cfg.gridDim = dim3(2 * std::min(max_clusters, p.total_units));
-    CTPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
-  } else {
-    const int grid = p.total_units < g_num_sms ? p.total_units : g_num_sms;
-    kernel<<<grid, kTcThreads, smem, st>>>(ta, tb, p);
   }
+  char label[128];
+  if (prof_enabled()) snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d p%d bn%d%s", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, p.planes, BN, MC ? " mc" : "");
+  ProfScope prof(label, 2.0 * p.B * p.H * p.W * (double)p.taps * p.Cin * p.Cout, st);
+  if (MC) cfg.gridDim = dim3(2 * std::min(max_clusters[dev], p.total_units));
+  else cfg.gridDim = dim3(std::min(p.total_units, g_sms[dev]));
+  CTPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
@@ -443,14 +511,13 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   CTPN_REQUIRE(B > 0 && H > 0 && W > 0, "ctpn_conv3x3: bad shape");
   const bool pool = flags & CTPN_F_POOL;
   CTPN_REQUIRE(!pool || (taps == 9 && H >= 2 && W >= 2), "ctpn_conv3x3: pooling needs taps=9 and H,W >= 2");
-  if (g_num_sms == 0) {
-    int dev = 0;
-    CTPN_CUDA(cudaGetDevice(&dev));
-    CTPN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  int dev = 0, rc;
+  CTPN_CUDA(cudaGetDevice(&dev));
+  CTPN_REQUIRE(dev >= 0 && dev < kMaxDevices, "ctpn_conv3x3: device index %d not supported", dev);
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_sms[dev] == 0) CTPN_CUDA(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   }
-  EncodeTiledFn enc = nullptr;
-  int rc = tma_get_encode(&enc);
-  if (rc) return rc;
 
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
@@ -476,11 +543,11 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.out = out;
   p.out_plane_stride = (long long)B * p.Ho * p.Wo * cout;
   p.cout_pad = cout;
-  p.debug = env_int("CTPN_TC_DEBUG", 0);
+  p.debug = tuning().debug;
 
   // N tile: 256 halves the A traffic per MAC but, with two accumulators per tile (P > 1), leaves no TMEM for
   // double buffering -- worth it only when the K loop is long enough to amortise the serialised epilogue.
-  int BN = env_int("CTPN_TC_BN", planes == 1 ? 256 : 128);
+  int BN = tuning().bn > 0 ? tuning().bn : (planes == 1 ? 256 : 128);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
   if (planes > 1 && BN > 128) BN = 128;   // main + cross accumulators, double buffered: 4 * BN TMEM columns <= 512
   while (BN > cout || cout % BN) BN >>= 1;
@@ -492,7 +559,7 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.total_tiles = (int)total;
   p.m_tiles = (int)m_tiles;
   // weight-tile multicast over 2-CTA clusters (3x3 layers with at least one pair of pixel tiles per SM pair)
-  const bool mc = taps == 9 && env_int("CTPN_TC_MCAST", 1) != 0 && m_tiles >= 2;
+  const bool mc = taps == 9 && tuning().mcast != 0 && m_tiles >= 2;
   p.total_units = mc ? (int)((m_tiles + 1) / 2) * p.tiles_n : p.total_tiles;
 
   CUtensorMap ta, tb;
@@ -501,19 +568,19 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
     cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes * B};
     cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.PW, (cuuint32_t)(p.TH + 2 * halo), 1};
-    if ((rc = tma_encode_bf16(enc, &ta, const_cast<void *>(in_planes), 4, dims, strides, box))) return rc;
+    if ((rc = cached_tmap(dev, &ta, in_planes, 4, dims, strides, box))) return rc;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)planes * cout};
     cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(mc ? BN / 2 : BN)};   // multicast: each CTA of the pair loads half the rows
-    if ((rc = tma_encode_bf16(enc, &tb, const_cast<void *>(w_planes), 2, dims, strides, box))) return rc;
+    if ((rc = cached_tmap(dev, &tb, w_planes, 2, dims, strides, box))) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
 #define CTPN_TC_CASE(BN_, P_, T_) \
-  if (BN == BN_ && planes == P_ && taps == T_) return launch_bn<BN_, P_, T_, 0>(ta, tb, p, st)
+  if (BN == BN_ && planes == P_ && taps == T_) return launch_bn<BN_, P_, T_, 0>(dev, ta, tb, p, st)
 #define CTPN_TC_CASE_MC(BN_, P_) \
-  if (mc && BN == BN_ && planes == P_) return launch_bn<BN_, P_, 9, 1>(ta, tb, p, st)
+  if (mc && BN == BN_ && planes == P_) return launch_bn<BN_, P_, 9, 1>(dev, ta, tb, p, st)
   CTPN_TC_CASE_MC(256, 1); CTPN_TC_CASE_MC(128, 1); CTPN_TC_CASE_MC(64, 1);
   CTPN_TC_CASE_MC(256, 2); CTPN_TC_CASE_MC(128, 2); CTPN_TC_CASE_MC(64, 2);
   CTPN_TC_CASE_MC(128, 3); CTPN_TC_CASE_MC(64, 3);

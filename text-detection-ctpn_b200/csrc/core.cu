@@ -31,6 +31,7 @@ struct ProfRec { std::string label; cudaEvent_t a, b; double work; };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_free_events;
 static bool g_prof_on = false;
+bool prof_enabled() { return g_prof_on; }
 static std::mutex g_prof_mu;
 
 static cudaEvent_t get_event() {

@@ -1,6 +1,6 @@
 // ctpn_net_*: the CTPN test graph up to the two head tensors, as one stream-ordered sequence of
 // the stage kernels (lib/networks/VGGnet_test.py:16-52; variable names per SURVEY.md App. A.2).
-//   uint8 image -> conv1_1 (SIMT, fused mean subtraction) -> 13 x tcgen05 conv (+fused pools)
+//   uint8 image -> conv1_1 (tcgen05, fused mean subtraction) -> 13 x tcgen05 conv (+fused pools)
 //   -> x-projection GEMM -> BiLSTM recurrence (2-CTA clusters) -> FC GEMM -> heads GEMM.
 // Weights live in library-owned device memory; activations in the caller's workspace.
 #include <algorithm>
@@ -9,6 +9,9 @@
 #include <vector>
 
 #include "common.cuh"
+#ifdef CTPN_DEBUG
+#include "testing/ctpn_b200_testing.h"
+#endif
 
 namespace ctpn {
 
@@ -214,8 +217,6 @@ extern "C" int ctpn_net_create(ctpn_net_t **net, int planes) {
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_net_create: planes must be 1..3 (got %d)", planes);
   ctpn_net *n = new ctpn_net();
   n->planes = planes;
-  if (const char *e = getenv("CTPN_CONV_IMPL")) n->conv_simt = strcmp(e, "simt") == 0;
-  if (const char *e = getenv("CTPN_CONV1_IMPL")) n->conv1_simt = strcmp(e, "simt") == 0;
   *net = n;
   return CTPN_OK;
 }
@@ -230,8 +231,10 @@ extern "C" int ctpn_net_destroy(ctpn_net_t *net) {
 extern "C" int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value) {
   CTPN_REQUIRE(net && key, "ctpn_net_set_option: null pointer");
   if (!strcmp(key, "keep_activations")) net->keep = value != 0;
+#ifdef CTPN_DEBUG   // float32 SIMT reference kernels: test library only
   else if (!strcmp(key, "conv_simt")) net->conv_simt = value != 0;
   else if (!strcmp(key, "conv1_simt")) net->conv1_simt = value != 0;
+#endif
   else { set_error("ctpn_net_set_option: unknown key '%s'", key); return CTPN_ERR_INVALID; }
   return CTPN_OK;
 }
@@ -270,20 +273,25 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
   char *ws = (char *)workspace;
   const int P = net->planes;
   net->taps.clear();
+#ifdef CTPN_DEBUG
   auto conv1 = (net->conv_simt || net->conv1_simt) ? ctpn_conv1_1 : ctpn_conv1_1_tc;
+  auto conv3 = net->conv_simt ? ctpn_conv3x3_simt : ctpn_conv3x3;
+#else
+  auto conv1 = ctpn_conv1_1_tc;
+  auto conv3 = ctpn_conv3x3;
+#endif
   if ((rc = conv1(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, P, stream))) return rc;
   net->taps["conv1_1"] = Tap{ws + L.act[0], (long long)B * H * W, 64, true};
   int h = H, w = W;
   for (int l = 1; l < 14; ++l) {
     const ConvSpec &s = kConvs[l];
     const int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0);
-    auto fn = net->conv_simt ? ctpn_conv3x3_simt : ctpn_conv3x3;
-    if ((rc = fn(ws + L.act[l - 1], net->conv_w[l], net->conv_b[l], ws + L.act[l], B, h, w, s.cin, s.cout, 9, P, flags, stream))) return rc;
+    if ((rc = conv3(ws + L.act[l - 1], net->conv_w[l], net->conv_b[l], ws + L.act[l], B, h, w, s.cin, s.cout, 9, P, flags, stream))) return rc;
     h = L.h[l]; w = L.w[l];
     net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] = Tap{ws + L.act[l], (long long)B * h * w, s.cout, true};
   }
   const int M = B * L.fh * L.fw;
-  auto gemm = net->conv_simt ? ctpn_conv3x3_simt : ctpn_conv3x3;
+  auto gemm = conv3;
   if ((rc = gemm(ws + L.act[13], net->xproj_w, net->xproj_b, ws + L.xproj, 1, 1, M, 512, 1024, 1, P, CTPN_F_OUT_F32, stream))) return rc;
   net->taps["xproj"] = Tap{ws + L.xproj, M, 1024, false};
   if ((rc = ctpn_bilstm_recurrent((const float *)(ws + L.xproj), net->wh_fw, net->wh_bw, ws + L.act[14], B * L.fh, L.fw, P, stream))) return rc;

@@ -412,8 +412,12 @@ extern "C" int ctpn_proposals(const float *cls, int cls_is_logit, const float *b
   ProfScope prof_all("proposals (decode+sort+nms+emit)", (double)batch * NA * 24.0, st);
   // column-wise NMS is possible when one column's boxes fit in shared memory and columns do not overlap
   const size_t col_smem = column_smem_bytes(H);
-  const bool try_columns = feat_stride >= 16 && col_smem <= 200 * 1024 && H * 10 <= 2048 && W <= 65535 &&
-                           !getenv("CTPN_GENERIC_NMS");
+#ifdef CTPN_DEBUG   // test library: force the generic bitmask NMS / the un-fused column gather (read once)
+  static const bool force_generic = getenv("CTPN_GENERIC_NMS") != nullptr, force_gather = getenv("CTPN_COLUMN_GATHER") != nullptr;
+#else
+  constexpr bool force_generic = false, force_gather = false;
+#endif
+  const bool try_columns = feat_stride >= 16 && col_smem <= 200 * 1024 && H * 10 <= 2048 && W <= 65535 && !force_generic;
   int *unstructured = (int *)(ws + w.unstructured);
   CTPN_CUDA(cudaMemsetAsync(unstructured, 0, (size_t)batch * sizeof(int), st));
   proposal_decode_kernel<<<g1, 256, 0, st>>>(cls, cls_is_logit, bbox, im_info, H, W, feat_stride, min_size,
@@ -422,7 +426,7 @@ extern "C" int ctpn_proposals(const float *cls, int cls_is_logit, const float *b
   CTPN_LAUNCH_CHECK();
   CTPN_CUDA(cudaFuncSetAttribute(proposal_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
   // W <= 256: the sort kernel also buckets the survivors by column (one more 8-bit pass)
-  const bool bucket = try_columns && W <= 256 && !getenv("CTPN_COLUMN_GATHER");
+  const bool bucket = try_columns && W <= 256 && !force_gather;
   int *col_start = (int *)(ws + w.col_start);
   proposal_sort_kernel<<<batch, kSortThreads, kSortSmem, st>>>(keys, valid, boxes, NA, max_n, (uint2 *)(ws + w.buf_a),
                                                        (uint2 *)(ws + w.buf_b), sorted_boxes, sorted_idx, counts,

@@ -1,28 +1,13 @@
-// float32 SIMT kernels around the tensor-core path:
-//   * ctpn_pack_weights   TF-layout float32 weights -> bf16 planes [P][Cout_pad][taps][Cin]
+// float32 SIMT reference kernels (test library only: libctpn_b200_dbg.so; not in the product library):
 //   * ctpn_conv1_1        first VGG layer (Cin = 3, K = 27: HBM-bound, no tensor cores); fuses the
 //                         uint8 -> float32 mean subtraction of lib/fast_rcnn/test.py:8-9
 //   * ctpn_conv3x3_simt   same contract as ctpn_conv3x3 with plain float32 FMAs: the in-library
 //                         reference the tests use to validate the tcgen05 kernel
 // Reference semantics: lib/networks/network.py:160-196.
-#include "common.cuh"
+#include "../common.cuh"
+#include "ctpn_b200_testing.h"
 
 namespace ctpn {
-
-// ---- weight packing ---------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float *__restrict__ w, int taps, int cin, int cout, int cout_pad,
-                                    int planes, __nv_bfloat16 *__restrict__ out) {
-  const long long n = (long long)cout_pad * taps * cin;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int ci = (int)(i % cin);
-  const int tap = (int)((i / cin) % taps);
-  const int co = (int)(i / ((long long)cin * taps));
-  float v = co < cout ? w[((long long)tap * cin + ci) * cout + co] : 0.f;
-  __nv_bfloat16 pl[3];
-  split_planes(v, planes, pl);
-  for (int p = 0; p < planes; ++p) out[(long long)p * n + i] = pl[p];
-}
 
 // ---- conv1_1 ----------------------------------------------------------------------------------
 // Lane = one pair of output channels (its 27 x 2 weights live in registers), warp = one tile row, and each
@@ -203,18 +188,6 @@ conv_simt_kernel(const __nv_bfloat16 *__restrict__ in, const __nv_bfloat16 *__re
 }  // namespace ctpn
 
 using namespace ctpn;
-
-extern "C" int ctpn_pack_weights(const float *w_tf, int taps, int cin, int cout, int cout_pad, int planes,
-                                 void *w_planes_out, void *stream) {
-  CTPN_REQUIRE(w_tf && w_planes_out, "ctpn_pack_weights: null pointer");
-  CTPN_REQUIRE(taps > 0 && cin > 0 && cout > 0 && cout_pad >= cout, "ctpn_pack_weights: bad shape");
-  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_pack_weights: planes must be 1..3");
-  const long long n = (long long)cout_pad * taps * cin;
-  pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      w_tf, taps, cin, cout, cout_pad, planes, reinterpret_cast<__nv_bfloat16 *>(w_planes_out));
-  CTPN_LAUNCH_CHECK();
-  return CTPN_OK;
-}
 
 extern "C" int ctpn_conv1_1(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
                             void *out_planes, int B, int H, int W, int planes, void *stream) {

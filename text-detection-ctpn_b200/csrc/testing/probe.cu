@@ -8,9 +8,10 @@
 // tensor core actually read.
 #include <cuda.h>
 
-#include "common.cuh"
-#include "tc_ptx.cuh"
-#include "tma_host.cuh"
+#include "../common.cuh"
+#include "../tc_ptx.cuh"
+#include "../tma_host.cuh"
+#include "ctpn_b200_testing.h"
 
 namespace ctpn {
 

@@ -9,6 +9,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctpn_b200.so")
+# CTPN_B200_LIB=dbg (tests only): the -DCTPN_DEBUG build with the SIMT reference kernels, the hardware probes and the
+# ablation / tuning environment switches (tests/_native/libctpn_b200_dbg.so, csrc/testing/ctpn_b200_testing.h)
+DEBUG_LIB = os.environ.get("CTPN_B200_LIB", "") == "dbg"
+if DEBUG_LIB:
+    LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "tests", "_native", "libctpn_b200_dbg.so")
 
 
 class CtpnError(RuntimeError):
@@ -48,10 +53,8 @@ SIGNATURES = {
     "ctpn_proposals_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "ctpn_proposals": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p]),
     "ctpn_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
-    "ctpn_conv1_1": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ctpn_conv1_1_tc": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ctpn_conv3x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "ctpn_conv3x3_simt": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ctpn_bilstm_recurrent": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "ctpn_net_create": (_i, [C.POINTER(_p), _i]),
     "ctpn_net_destroy": (_i, [_p]),
@@ -60,13 +63,20 @@ SIGNATURES = {
     "ctpn_net_workspace_bytes": (_z, [_p, _i, _i, _i]),
     "ctpn_net_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _z, _p]),
     "ctpn_net_feature_hw": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
-    "ctpn_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _i, _p]),
-    "ctpn_probe_mma_rate_pair": (_i, [_i, _i, _i, _i, _p]),
-    "ctpn_probe_umma_view": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "ctpn_net_debug_tap": (_i, [_p, C.c_char_p, _p, _z, C.POINTER(_z), _p]),
 }
 
-for _name, (_res, _args) in SIGNATURES.items():
+# test library only (csrc/testing/ctpn_b200_testing.h)
+TESTING_SIGNATURES = {
+    "ctpn_conv1_1": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ctpn_conv3x3_simt": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ctpn_probe_mma_rate": (_i, [_i, _i, _i, _i, _i, _i, _i, _p]),
+    "ctpn_probe_mma_rate_pair": (_i, [_i, _i, _i, _i, _p]),
+    "ctpn_probe_mma_kind": (_i, [_i, _i, _i, _i, _i, _p]),
+    "ctpn_probe_umma_view": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+}
+
+for _name, (_res, _args) in list(SIGNATURES.items()) + (list(TESTING_SIGNATURES.items()) if DEBUG_LIB else []):
     _fn = getattr(lib, _name)      # AttributeError here == header/library mismatch
     _fn.restype = _res
     _fn.argtypes = _args

@@ -39,7 +39,7 @@ class Engine:
         h = C.c_void_p()
         N.check(N.lib.ctpn_net_create(C.byref(h), self.planes), "ctpn_net_create")
         self._net = h
-        if conv_simt:
+        if conv_simt:          # float32 SIMT reference convolutions: only in the test library (CTPN_B200_LIB=dbg)
             N.check(N.lib.ctpn_net_set_option(self._net, b"conv_simt", 1), "set_option")
         if keep_activations:
             N.check(N.lib.ctpn_net_set_option(self._net, b"keep_activations", 1), "set_option")
