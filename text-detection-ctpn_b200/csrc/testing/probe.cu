@@ -235,9 +235,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_e4m3(int M, int N) {   // kind
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN, int PAIR>
+template <int BN, int PAIR, int MODE>
 __global__ void __launch_bounds__(128, 1)
-probe_mma_kind_kernel(int n_mma, int mode) {
+probe_mma_kind_kernel(int n_mma) {
+  constexpr int mode = MODE;     // compile time: the unrolled issue loop has no branches
   using namespace ptx;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -323,7 +324,7 @@ extern "C" int ctpn_probe_mma_kind(int bn, int pair, int mode, int n_mma, int gr
   cudaStream_t st = (cudaStream_t)stream;
 #define CTPN_LAUNCH_KIND(BN, PAIR)                                                                                 \
   do {                                                                                                             \
-    auto k = probe_mma_kind_kernel<BN, PAIR>;                                                                      \
+    auto k = mode == 0 ? probe_mma_kind_kernel<BN, PAIR, 0> : mode == 1 ? probe_mma_kind_kernel<BN, PAIR, 1> : probe_mma_kind_kernel<BN, PAIR, 2>; \
     CTPN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
     cudaLaunchConfig_t cfg = {};                                                                                   \
     cudaLaunchAttribute attr;                                                                                      \
@@ -331,7 +332,7 @@ extern "C" int ctpn_probe_mma_kind(int bn, int pair, int mode, int n_mma, int gr
     attr.val.clusterDim.x = PAIR ? 2 : 1; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;                    \
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;              \
     cfg.attrs = &attr; cfg.numAttrs = 1;                                                                           \
-    CTPN_CUDA(cudaLaunchKernelEx(&cfg, k, n_mma, mode));                                                           \
+    CTPN_CUDA(cudaLaunchKernelEx(&cfg, k, n_mma));                                                           \
   } while (0)
   if (pair) {
     if (bn == 256) CTPN_LAUNCH_KIND(256, 1); else if (bn == 128) CTPN_LAUNCH_KIND(128, 1); else CTPN_LAUNCH_KIND(64, 1);

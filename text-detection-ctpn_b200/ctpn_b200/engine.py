@@ -77,9 +77,12 @@ class Engine:
         return buf
 
     def _pin(self, key, shape, dtype):
+        key = (key, tuple(shape), dtype)       # one buffer per use AND shape: alternating shape buckets never re-pin
         t = self._pinned.get(key)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        if t is None:
+            if len(self._pinned) >= 64:
+                self._pinned.clear()
+            t = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
             self._pinned[key] = t
         return t
 
@@ -333,6 +336,39 @@ class Engine:
             k += 1
         if pending is not None:
             yield finish(pending)
+
+    def detect_lines_batches(self, batches, mode="H", im_info=None, workers=8, gather=False, cfg=None):
+        """The whole ctpn() call chain (demo.py:55-68 minus file I/O) for a stream of host batches: rois_batches() on the
+        GPU, then TextDetector.detect of every image in the library's host connector (ctpn_text_lines_host, which
+        releases the GIL) on a pool of `workers` threads, one batch behind the GPU.  Yields, per batch, a list of
+        float64 [m,9] text-line arrays (x1,y1,x2,y2,x3,y3,x4,y4,score) in the frame of the blob divided by im_scale."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .textlines import text_lines
+
+        def lines_of(rois, size, scale):
+            return text_lines(rois[:, 1:5] / np.float32(scale), rois[:, 0], size, mode, cfg)
+
+        batches = iter(batches)
+        shapes = []
+
+        def tracked():
+            for b in batches:
+                shapes.append(tuple(b.shape[1:3]))
+                yield b
+
+        pool = getattr(self, "_line_pool", None)
+        if pool is None or pool._max_workers != workers:
+            pool = self._line_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="ctpn-lines")
+        pending = None
+        for k, rois_list in enumerate(self.rois_batches(tracked(), im_info=im_info, gather=gather)):
+            H, W = shapes[k]
+            scale = 1.0 if im_info is None else float(np.asarray(im_info, np.float32).reshape(-1, 3)[0, 2])
+            futs = [pool.submit(lines_of, r, (int(round(H / scale)), int(round(W / scale))), scale) for r in rois_list]
+            if pending is not None:
+                yield [f.result() for f in pending]
+            pending = futs
+        if pending is not None:
+            yield [f.result() for f in pending]
 
     def detect_batch(self, images, im_scale=1.0):
         """Returns a list of (scores [n] f32, boxes [n,4] f32) per image, boxes divided by
