@@ -48,6 +48,8 @@ CONFIGS = {
 MODES = {
     "bf16": dict(planes=1, units=1.0, dtype="bf16 operands, fp32 accumulate"),
     "bf16x2": dict(planes=2, units=3.0, dtype="fp32-faithful: bf16x2 split operands (3 tcgen05 MMAs per MAC), fp32 accumulate"),
+    "f16f8": dict(planes=4, units=2.0, dtype="fp32-faithful: fp16 operands + e4m3 cross terms (1 kind::f16 + 1 kind::f8f6f4 tcgen05 MMA per 16 MACs: "
+                                             "2 bf16-rate units per MAC), fp32 accumulate; matmuls around the BiLSTM on bf16x2"),
     "bf16x3": dict(planes=3, units=6.0, dtype="fp32-equivalent: bf16x3 split operands (6 tcgen05 MMAs per MAC), fp32 accumulate"),
 }
 FP32_MODE = os.environ.get("CTPN_BENCH_FP32_MODE", "bf16x2")     # the mode configs 2/4/5 run in

@@ -105,8 +105,28 @@ int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const flo
 #define CTPN_F_RELU 1
 #define CTPN_F_POOL 2
 #define CTPN_F_OUT_F32 4
+#define CTPN_F_OUT_BF16X2 8 /* ctpn_conv3x3_f16f8 only: write two bf16 planes instead of F16F8 planes */
 int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B,
                  int H, int W, int cin, int cout, int taps, int planes, int flags, void *stream);
+/* The same layers in the "F16F8" arithmetic: 2 tensor-core units per MAC instead of the 3 of two bf16 planes, float32-faithful
+ * to ~5e-4 on the head logits.  A value a is carried as h = fp16(a * s) plus e4m3 copies of a and of the exact
+ * residual a * s - h; products are h_a * h_w on kind::f16 MMAs plus the two cross terms on kind::f8f6f4 MMAs.
+ * Activation planes: [0] fp16 [B][H][W][C]; [1] per pixel and 64-channel block 128 bytes e4m3(a * t)[64] | e4m3(r * 2^11 t / s)[64].
+ * Weight planes (ctpn_pack_weights_f16f8): [0] fp16(w * s_w) [Cout][taps][Cin]; [1] per (cout, tap, 64-channel block)
+ * e4m3(r_w * 2^11 t_w / s_w)[64] | e4m3(w * t_w)[64].  All scales are powers of two chosen by the caller (per tensor).
+ * ctpn_conv3x3_f16f8: value = main * inv_main + cross * inv_cross with inv_main = 1 / (s_in * s_w) and
+ * inv_cross = 1 / (2^11 * t_in * t_w); outputs are quantised with out_s / out_t (F16F8 planes), or written as float32
+ * (CTPN_F_OUT_F32) or as two bf16 planes (CTPN_F_OUT_BF16X2).  Same shape rules and flags as ctpn_conv3x3. */
+int ctpn_pack_weights_f16f8(const float *w_tf, int taps, int cin, int cout, int cout_pad, float s_w, float t_w,
+                            void *w_planes_out, void *stream);
+int ctpn_conv3x3_f16f8(const void *in_planes, const void *w_planes, const float *bias, void *out, int B, int H, int W,
+                       int cin, int cout, int taps, int flags, float inv_main, float inv_cross, float out_s, float out_t,
+                       void *stream);
+
+/* conv1_1 writing F16F8 planes (the layer itself multiplies two bf16 planes; K = 27). */
+int ctpn_conv1_1_tc_f16f8(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                          void *out_planes, int B, int H, int W, float out_s, float out_t, void *stream);
+
 /* BiLSTM recurrence (network.py:97-101).  xproj: float32 [R][W][1024] = x.Wx + b for
  * (fw gates i,j,f,o | bw gates i,j,f,o); wh_fw / wh_bw: float32 [128][512] recurrent kernels
  * (rows 512..639 of the TF kernel).  Output planes [P][R][W][256] = concat(h_fw, h_bw). */
@@ -115,10 +135,15 @@ int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, const float *w
 
 /* ---- whole network up to the head tensors -------------------------------------------- */
 typedef struct ctpn_net ctpn_net_t;
+/* planes: 1..3 bf16 planes, or CTPN_ARITH_F16F8: conv1_1 + the thirteen 3x3 layers in the 2-unit F16F8 arithmetic (the
+ * matmuls around the BiLSTM stay on two bf16 planes).  F16F8 activation scales are calibrated on the first batch that
+ * ctpn_net_forward sees and then frozen (option "recalibrate" re-arms the calibration). */
+#define CTPN_ARITH_F16F8 4
 int ctpn_net_create(ctpn_net_t **net, int planes);
 int ctpn_net_destroy(ctpn_net_t *net);
 /* options: "keep_activations" (1: every layer gets its own workspace region so that
- * ctpn_net_debug_tap can read all of them after a forward). */
+ * ctpn_net_debug_tap can read all of them after a forward), "recalibrate" (F16F8: re-derive the activation scales from
+ * the next batch). */
 int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value);
 /* name = TF variable name; data = host float32 in TF layout. */
 int ctpn_net_set_weight(ctpn_net_t *net, const char *name, const float *data_host, size_t count);

@@ -86,6 +86,99 @@ def cmd_conv(a):
     return 0 if ok else 1
 
 
+def _pow2_floor(v):
+    return float(2.0 ** np.floor(np.log2(v)))
+
+
+def f16f8_quantize(x, s, t):
+    """float32 tensor [..., C] (C % 64 == 0) -> (fp16 plane, uint8 cross plane [..., C/64, 128], dequantised (h, v8, r8) as
+    float64) under the F16F8 rules of csrc/common.cuh: h = fp16(x s), v8 = e4m3(x t), r8 = e4m3((x s - h) 2^11 t / s)."""
+    import torch
+    h = (x * s).to(torch.float16)
+    r = x * s - h.float()
+    v8 = (x * t).clamp(-448, 448).to(torch.float8_e4m3fn)
+    r8 = (r * (2048.0 * t / s)).clamp(-448, 448).to(torch.float8_e4m3fn)
+    lead = x.shape[:-1]
+    C = x.shape[-1]
+    cross = torch.cat([v8.view(torch.uint8).reshape(lead + (C // 64, 64)), r8.view(torch.uint8).reshape(lead + (C // 64, 64))], dim=-1)
+    return h, cross.contiguous(), (h.double() / s, v8.double() / t, r8.double() / (2048.0 * t))
+
+
+def cmd_conv_f16f8(a):
+    """ctpn_conv3x3_f16f8 against a float64 evaluation of exactly the operand values the planes carry:
+    y = conv(h_a, h_w) + conv(q(a), q(r_w)) + conv(q(r_a), q(w)) (+bias, ReLU, pool), for float32, F16F8 and bf16x2 outputs;
+    also checks the device weight packer bit for bit."""
+    import torch
+    from ctpn_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(a.seed)
+    x = torch.relu(torch.randn(a.B, a.H, a.W, a.cin, generator=g)) * a.xscale
+    w = torch.randn(a.taps, a.cin, a.cout, generator=g) * (2.0 / (a.taps * a.cin)) ** 0.5
+    b = torch.randn(a.cout, generator=g) * 0.1
+    s_in, t_in = 1.0, _pow2_floor(448.0 / float(x.abs().max())) / 2.0
+    s_w, t_w = _pow2_floor(16384.0 / float(w.abs().max())), _pow2_floor(448.0 / float(w.abs().max()))
+    xh, xc, (xh_d, xv_d, xr_d) = f16f8_quantize(x, s_in, t_in)
+    inp = torch.cat([xh.view(torch.uint8).reshape(-1), xc.reshape(-1)]).to(dev)
+    # weights: device packer vs the same rules in torch, on [Cout][taps][Cin]
+    wt = w.permute(2, 0, 1).contiguous()
+    wh, wc, (wh_d, wv_d, wr_d) = f16f8_quantize(wt, s_w, t_w)
+    # weight cross rows are residual-first: swap the halves of every 128-byte block
+    wc = torch.cat([wc[..., 64:], wc[..., :64]], dim=-1).contiguous()
+    want_w = torch.cat([wh.view(torch.uint8).reshape(-1), wc.reshape(-1)])
+    wp = torch.zeros(want_w.numel(), dtype=torch.uint8, device=dev)
+    w_dev, b_dev = w.to(dev).contiguous(), b.to(dev).contiguous()
+    N.check(N.lib.ctpn_pack_weights_f16f8(N.ptr(w_dev), a.taps, a.cin, a.cout, a.cout, s_w, t_w, N.ptr(wp), N.stream_ptr()), "pack")
+    torch.cuda.synchronize()
+    pack_ok = bool(torch.equal(wp.cpu(), want_w))
+    # float64 reference on the carried values
+    k = 3 if a.taps == 9 else 1
+
+    def conv64(xd, wd):
+        return torch.nn.functional.conv2d(xd.to(dev).permute(0, 3, 1, 2), wd.to(dev).view(a.cout, k, k, a.cin).permute(0, 3, 1, 2), None, padding=k // 2)
+    y = conv64(xh_d, wh_d) + conv64(xv_d, wr_d) + conv64(xr_d, wv_d) + b_dev.double().view(1, -1, 1, 1)
+    if a.flags & F_RELU:
+        y = torch.relu(y)
+    pool = bool(a.flags & F_POOL)
+    if pool:
+        y = torch.nn.functional.max_pool2d(y, 2, 2)
+    y = y.permute(0, 2, 3, 1).contiguous()
+    Ho, Wo = y.shape[1], y.shape[2]
+    scale = y.abs().max().item()
+    inv_main, inv_cross = 1.0 / (s_in * s_w), 1.0 / (2048.0 * t_in * t_w)
+    out_s, out_t = 1.0, _pow2_floor(448.0 / max(scale, 1e-6)) / 2.0
+    res = {"pack_ok": pack_ok}
+
+    def run(flags, out):
+        N.check(N.lib.ctpn_conv3x3_f16f8(N.ptr(inp), N.ptr(wp), N.ptr(b_dev), N.ptr(out), a.B, a.H, a.W, a.cin, a.cout, a.taps, flags,
+                                         inv_main, inv_cross, out_s, out_t, N.stream_ptr()), "conv_f16f8")
+        torch.cuda.synchronize()
+    # (1) float32 output: only accumulation error
+    o32 = torch.full((a.B, Ho, Wo, a.cout), float("nan"), dtype=torch.float32, device=dev)
+    run(a.flags | F_F32, o32)
+    e32 = (o32.double() - y).abs().max().item()
+    res.update(f32_err=e32, scale=scale, f32_nan=int(torch.isnan(o32).sum().item()))
+    # (2) F16F8 planes
+    nel = a.B * Ho * Wo * a.cout
+    oq = torch.zeros(nel * 4, dtype=torch.uint8, device=dev)
+    run(a.flags, oq)
+    h = oq[:nel * 2].view(torch.float16).double().view(a.B, Ho, Wo, a.cout)
+    cr = oq[nel * 2:].view(a.B, Ho, Wo, a.cout // 64, 128)
+    v8 = cr[..., :64].contiguous().view(torch.float8_e4m3fn).double().reshape(a.B, Ho, Wo, a.cout) / out_t
+    r8 = cr[..., 64:].contiguous().view(torch.float8_e4m3fn).double().reshape(a.B, Ho, Wo, a.cout) / (2048.0 * out_t)
+    eq_hr = ((h / out_s + r8) - y).abs().max().item()        # value + residual: ~2^-16 relative
+    eq_v8 = ((v8 - y).abs() / (y.abs() + scale * 2.0 ** -9)).max().item()     # e4m3 copy: 2^-4 relative (+ subnormal floor)
+    res.update(q_err_h_plus_r=eq_hr, q_rel_err_e4m3=eq_v8)
+    # (3) two bf16 planes
+    ob = torch.zeros((2, a.B, Ho, Wo, a.cout), dtype=torch.bfloat16, device=dev)
+    run(a.flags | 8, ob)
+    eb = (ob.double().sum(0) - y).abs().max().item()
+    res.update(bf16x2_err=eb)
+    ok = (pack_ok and res["f32_nan"] == 0 and e32 <= 2e-5 * scale and eq_hr <= 6e-5 * scale and eq_v8 <= 0.07 and eb <= 4e-5 * scale)
+    res["ok"] = bool(ok)
+    print(json.dumps(res))
+    return 0 if ok else 1
+
+
 def cmd_conv1(a):
     """conv1_1 (tensor-core im2col-in-smem kernel or the SIMT one) against float64 on the same uint8 image."""
     import torch
@@ -197,13 +290,17 @@ def main():
     l = sub.add_parser("bilstm")
     for k, d in dict(R=37, W=56, planes=2, seed=0).items():
         l.add_argument("--" + k, type=int, default=d)
+    cq = sub.add_parser("conv_f16f8")
+    for k, d in dict(B=1, H=8, W=16, cin=64, cout=64, taps=9, flags=0, seed=0).items():
+        cq.add_argument("--" + k, type=int, default=d)
+    cq.add_argument("--xscale", type=float, default=1.0)
     ns = sub.add_parser("net_simt")
     for k, d in dict(B=3, H=128, W=192, planes=2).items():
         ns.add_argument("--" + k, type=int, default=d)
     ns.add_argument("--tol", type=float, default=5e-4)
     sub.add_parser("proposals_generic")
     a = ap.parse_args()
-    return {"conv": cmd_conv, "conv1": cmd_conv1, "bilstm": cmd_bilstm, "net_simt": cmd_net_simt,
+    return {"conv": cmd_conv, "conv_f16f8": cmd_conv_f16f8, "conv1": cmd_conv1, "bilstm": cmd_bilstm, "net_simt": cmd_net_simt,
             "proposals_generic": cmd_proposals_generic}[a.cmd](a)
 
 

@@ -61,6 +61,25 @@ def test_conv_tcgen05_single_cta_variant(case):
     run_check(*conv_args(*case), env=dict(DBG, CTPN_TC_MCAST="0"))
 
 
+# (B, H, W, cin, cout, taps, flags, xscale)
+F16F8_CASES = [
+    (1, 8, 16, 64, 64, 9, RELU, 1.0),             # one tile
+    (2, 37, 56, 128, 128, 9, RELU, 1.0),          # ragged conv5-sized map, 2-CTA multicast path
+    (1, 37, 56, 512, 512, 9, RELU, 4.0),          # K = 4608, four N tiles
+    (3, 75, 112, 64, 64, 9, RELU | POOL, 30.0),   # fused pool, BN = 64, large activations
+    (1, 150, 225, 64, 128, 9, RELU, 0.05),        # many tiles per CTA, small activations
+    (1, 1, 2072, 512, 1024, 1, 0, 1.0),           # 1x1 GEMM (no ReLU: signed outputs)
+]
+
+
+@pytest.mark.parametrize("case", F16F8_CASES, ids=lambda c: "B%d_%dx%d_c%d-%d_t%d_f%d_x%g" % c)
+def test_conv_f16f8(case):
+    """The 2-unit arithmetic (fp16 main + e4m3 cross terms) against float64 on the carried operand values; float32, F16F8
+    and bf16x2 outputs; device weight packer bit-exact against the same rules in torch."""
+    B, H, W, cin, cout, taps, flags, xs = case
+    run_check("conv_f16f8", "--B", B, "--H", H, "--W", W, "--cin", cin, "--cout", cout, "--taps", taps, "--flags", flags, "--xscale", xs)
+
+
 SIMT_CASES = [
     (1, 13, 17, 64, 64, 9, 2, RELU),
     (2, 20, 30, 64, 128, 9, 3, RELU | POOL),

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -78,6 +79,35 @@ __device__ __forceinline__ void split_planes2(float a, float b, uint32_t (&w)[P]
       b = __fsub_rn(b, __uint_as_float(pk & 0xffff0000u));
     }
   }
+}
+
+// ---- "F16F8" operand format (2 tensor-core units per MAC instead of the 3 of two bf16 planes) -----------------------
+// A float32 value a is carried as  h = fp16_rn(a * s)  (11 significant bits) and its exact residual  r = a * s - h
+// (|r| <= 2^-11 |h|).  A product a * w = (h_a + r_a)(h_w + r_w) / (s_a s_w) is evaluated as
+//     main  = h_a * h_w                          kind::f16 MMA (fp16 x fp16, exact products, fp32 accumulate): 1 unit
+//     cross = q(h_a) * q(r_w) + q(r_a) * q(h_w)   kind::f8f6f4 MMA on e4m3 copies, K-concatenated: 2 x 1/2 unit
+// (r_a * r_w ~ 2^-22 is dropped).  Storage per element: 2 B (h) + 1 B (e4m3 of a) + 1 B (e4m3 of r) = the 4 B of two bf16
+// planes.  The e4m3 copies use per-tensor power-of-two scales t (values) and 2^11 t (residuals) so that both cross
+// products carry the same scale: e4m3(a t_a) * e4m3(r_w 2^11 t_w) and e4m3(r_a 2^11 t_a) * e4m3(w t_w).
+// Plane 0: fp16 [B][H][W][C].  Plane 1, per pixel and 64-channel block, 128 bytes: e4m3(a t)[64] | e4m3(r 2^11 t / s)[64]
+// -- one 128-byte swizzle row = K 128 of the fp8 MMA (4 instructions of K = 32).
+constexpr float kResidualGain = 2048.0f;      // 2^11
+
+// (a, b) -> fp16x2 word (a in the low half), saturating; ra/rb receive the exact residuals a - h_a, b - h_b
+__device__ __forceinline__ uint32_t f16x2_split(float a, float b, float &ra, float &rb) {
+  uint32_t pk;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(b), "f"(a));   // first source -> upper half
+  const __half2 h = *reinterpret_cast<const __half2 *>(&pk);
+  ra = __fsub_rn(a, __low2float(h));
+  rb = __fsub_rn(b, __high2float(h));
+  return pk;
+}
+// four floats -> four e4m3 bytes (a in the lowest byte), saturating to +-448
+__device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {

@@ -42,9 +42,12 @@ struct Conv1TcParams {
   int tiles_x, tiles_y, total_tiles;
   int debug;   // test library only (CTPN_C1_DEBUG bits): 1 skip patch staging, 2 skip tile build, 4 skip stores, 8 skip epilogue math
   long long plane_stride;
+  float out_s, out_t, out_rs;    // OUTQ: F16F8 output quantisation (common.cuh), out_rs = 2^11 * out_t / out_s
 };
 
-template <int P>
+// OUTQ = 1: the output is written in the F16F8 activation format (fp16 plane + e4m3 value / residual plane) for a
+// conv1_2 that runs in the 2-unit arithmetic; the layer itself still multiplies P bf16 planes (K = 27: the MMAs are free).
+template <int P, int OUTQ>
 __global__ void __launch_bounds__(kC1tThreads, 1)
 conv1_tc_kernel(const Conv1TcParams p) {
   using namespace ptx;
@@ -275,6 +278,40 @@ conv1_tc_kernel(const Conv1TcParams p) {
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
         }
         // the bias came in through the tensor core (k = 27 row of the weight tile x the builders' constant 1)
+        if (OUTQ) {
+          uint32_t wh[16], wq[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v0 = fmaxf(v[4 * i], 0.f), v1 = fmaxf(v[4 * i + 1], 0.f), v2 = fmaxf(v[4 * i + 2], 0.f), v3 = fmaxf(v[4 * i + 3], 0.f);
+            float r0, r1, r2, r3;
+            wh[2 * i] = f16x2_split(v0 * p.out_s, v1 * p.out_s, r0, r1);
+            wh[2 * i + 1] = f16x2_split(v2 * p.out_s, v3 * p.out_s, r2, r3);
+            wq[i] = e4m3x4(v0 * p.out_t, v1 * p.out_t, v2 * p.out_t, v3 * p.out_t);
+            wq[8 + i] = e4m3x4(r0 * p.out_rs, r1 * p.out_rs, r2 * p.out_rs, r3 * p.out_rs);
+          }
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 val = pl == 0 ? make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3])
+                                        : make_uint4(wq[4 * q], wq[4 * q + 1], wq[4 * q + 2], wq[4 * q + 3]);
+              stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = val;
+            }
+            __syncwarp();
+            // plane 0: 32 fp16 = 64 contiguous bytes per pixel; plane 1: values at +chunk*32, residuals at +64+chunk*32 of
+            // the pixel's single 128-byte block (Cout = 64)
+            uint8_t *obase = reinterpret_cast<uint8_t *>(p.out) + (long long)pl * p.plane_stride * 2;
+            const int j = lane & 3;
+            const int off = pl == 0 ? chunk * 64 + j * 16 : chunk * 32 + (j >> 1) * 64 + (j & 1) * 16;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int pp = it * 8 + (lane >> 2);
+              const uint4 val = stage_w[pp * 4 + (j ^ ((pp >> 1) & 3))];
+              if (((okmask >> pp) & 1u) && !C1_DBG(p, 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 128 + off) = val;
+            }
+          }
+        } else {
         uint32_t w[P][16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -297,6 +334,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
             if (((okmask >> pp) & 1u) && !C1_DBG(p, 4)) *reinterpret_cast<uint4 *>(obase + spix[it] * 64) = val;
           }
         }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -312,7 +350,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
   }
 }
 
-template <int P>
+template <int P, int OUTQ = 0>
 static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)(P <= 2 ? 4 : 2) * P * kC1tTileBytes + (size_t)P * 64 * 128 + (4 * kC1tPatch + 768) * sizeof(float) +
                       8 * 32 * kC1tStagePitch + 96 + 16;
@@ -326,24 +364,20 @@ static int launch_conv1_tc(Conv1TcParams &p, cudaStream_t st) {
   {
     std::lock_guard<std::mutex> lock(mu);
     if (sm_count[dev] == 0) {
-      CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CTPN_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<P, OUTQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CTPN_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     }
     sms = sm_count[dev];
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   ProfScope prof("conv1_1", 2.0 * p.B * p.H * p.W * 27.0 * 64.0, st);
-  conv1_tc_kernel<P><<<grid, kC1tThreads, smem, st>>>(p);
+  conv1_tc_kernel<P, OUTQ><<<grid, kC1tThreads, smem, st>>>(p);
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
 
-}  // namespace ctpn
-
-using namespace ctpn;
-
-extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
-                               void *out_planes, int B, int H, int W, int planes, void *stream) {
+static int conv1_tc_run(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                        void *out_planes, int B, int H, int W, int planes, bool outq, float out_s, float out_t, void *stream) {
   CTPN_REQUIRE(src && w_hwio && bias && out_planes, "ctpn_conv1_1_tc: null pointer");
   CTPN_REQUIRE(src_is_f32 || lut, "ctpn_conv1_1_tc: uint8 input needs the mean-subtraction LUT");
   CTPN_REQUIRE(B > 0 && H > 0 && W > 0, "ctpn_conv1_1_tc: bad shape");
@@ -356,6 +390,11 @@ extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut
   CTPN_REQUIRE(total < (1ll << 31), "ctpn_conv1_1_tc: too many tiles");
   p.total_tiles = (int)total;
   p.plane_stride = (long long)B * H * W * 64;
+  p.out_s = p.out_t = p.out_rs = 1.f;
+  if (outq) {
+    CTPN_REQUIRE(out_s > 0.f && out_t > 0.f, "ctpn_conv1_1_tc_f16f8: scales must be positive");
+    p.out_s = out_s; p.out_t = out_t; p.out_rs = kResidualGain * out_t / out_s;
+  }
 #ifdef CTPN_DEBUG
   static const int dbg = [] { const char *e = getenv("CTPN_C1_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
@@ -363,7 +402,22 @@ extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut
   p.debug = 0;
 #endif
   cudaStream_t st = (cudaStream_t)stream;
+  if (outq) return launch_conv1_tc<2, 1>(p, st);
   if (planes == 1) return launch_conv1_tc<1>(p, st);
   if (planes == 2) return launch_conv1_tc<2>(p, st);
   return launch_conv1_tc<3>(p, st);
+}
+
+}  // namespace ctpn
+
+using namespace ctpn;
+
+extern "C" int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                               void *out_planes, int B, int H, int W, int planes, void *stream) {
+  return conv1_tc_run(src, src_is_f32, lut, w_hwio, bias, out_planes, B, H, W, planes, false, 1.f, 1.f, stream);
+}
+
+extern "C" int ctpn_conv1_1_tc_f16f8(const void *src, int src_is_f32, const float *lut, const float *w_hwio, const float *bias,
+                                     void *out_planes, int B, int H, int W, float out_s, float out_t, void *stream) {
+  return conv1_tc_run(src, src_is_f32, lut, w_hwio, bias, out_planes, B, H, W, 2, true, out_s, out_t, stream);
 }

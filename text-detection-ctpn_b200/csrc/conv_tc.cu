@@ -60,6 +60,9 @@ struct ConvTcParams {
   const float *bias;
   void *out;
   long long out_plane_stride;   // elements between output planes
+  // F16F8 arithmetic (common.cuh): value = main * inv_main + cross * inv_cross; outputs are re-quantised as
+  // h = fp16(v * out_s), e4m3(v * out_t), e4m3((v * out_s - h) * out_rs) with out_rs = 2^11 * out_t / out_s
+  float inv_main, inv_cross, out_s, out_t, out_rs;
 };
 
 constexpr int kTcThreads = 352;   // warps: 0 B-producer, 1 MMA, 2-5 epilogue set 0, 6 A-producer, 7-10 epilogue set 1
@@ -83,13 +86,18 @@ __device__ __forceinline__ uint64_t umma_desc_a_view(uint32_t smem_addr, uint32_
 // lock step; each loads half of every weight (B) tile and TMA-multicasts it into both CTAs' shared memory, which halves the
 // L2 -> SM weight traffic (86 % of the kernel's L2 reads).  A weight stage is free when BOTH CTAs' MMAs have read it, so
 // its 'empty' barrier counts two multicast tcgen05.commit arrivals.
-template <int BN, int P, int TAPS, int MC>
+// F8 = 1 (with P = 2 stage slots): the F16F8 arithmetic -- plane 0 holds fp16 operands (kind::f16 MMAs into the main
+// accumulator), plane 1 the K-concatenated e4m3 copies (kind::f8f6f4 MMAs, K = 32, into the cross accumulator): 4 + 4 tensor
+// core instructions per (tap, channel block) where two bf16 planes need 12.
+template <int BN, int P, int TAPS, int MC, int F8>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const ConvTcParams p) {
   using namespace ptx;
   constexpr int kBBytes = BN * 128;
-  constexpr uint32_t kIdesc = umma_idesc_bf16(128, BN);
+  static_assert(!F8 || P == 2, "F16F8 uses two stage slots per operand");
+  constexpr uint32_t kIdesc = F8 ? umma_idesc_f16(128, BN) : umma_idesc_bf16(128, BN);
+  constexpr uint32_t kIdesc8 = umma_idesc_e4m3(128, BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring_a = (raw + 1023u) & ~1023u;
@@ -226,7 +234,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             constexpr int kPW = 10;
             const uint32_t view16 = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + tap % 3) * 8u : 0u;
             const uint32_t not_first = (kb | tap) != 0;
-            if (elect_one() && !CTPN_DBG(p, 4)) {
+            if (F8) {
+              if (elect_one() && !CTPN_DBG(p, 4)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // fp16 x fp16, K = 16 (32 B) per instruction
+                  mma_bf16_ss(d_main, ((uint64_t)hi_a << 32) | (a_lo + view16 + 2u * k), ((uint64_t)kHiB << 32) | (b_lo + 2u * k), kIdesc,
+                              k == 0 ? not_first : 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)     // e4m3 x e4m3, K = 32 (32 B): k 0,1 = value x residual, k 2,3 = residual x value
+                  mma_f8_ss(d_cross, ((uint64_t)hi_a << 32) | (a_lo + kPatch16 + view16 + 2u * k),
+                            ((uint64_t)kHiB << 32) | (b_lo + kB16 + 2u * k), kIdesc8, k == 0 ? not_first : 1u);
+              }
+            } else if (elect_one() && !CTPN_DBG(p, 4)) {
 #pragma unroll
               for (int i = 0; i < P; ++i) {
 #pragma unroll
@@ -310,8 +329,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t rc[32];
           tmem_ld_32x32(taddr + BN + chunk * 32, rc);
           tmem_ld_wait();
+          if (F8) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + __uint_as_float(rc[i]);
+            for (int i = 0; i < 32; ++i) v[i] = __fmaf_rn(__uint_as_float(rc[i]), p.inv_cross, __uint_as_float(rr[i]) * p.inv_main);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + __uint_as_float(rc[i]);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
@@ -335,7 +359,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], p.TW));
           }
         }
-        if (!out_f32) {
+        if (F8 && !out_f32 && !(p.flags & CTPN_F_OUT_BF16X2)) {
+          // F16F8 planes: fp16 words, then the e4m3 copies of the values and of the residuals (8 + 8 words)
+          uint32_t wh[16], wq[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float r0, r1, r2, r3;
+            wh[2 * i] = f16x2_split(v[4 * i] * p.out_s, v[4 * i + 1] * p.out_s, r0, r1);
+            wh[2 * i + 1] = f16x2_split(v[4 * i + 2] * p.out_s, v[4 * i + 3] * p.out_s, r2, r3);
+            wq[i] = e4m3x4(v[4 * i] * p.out_t, v[4 * i + 1] * p.out_t, v[4 * i + 2] * p.out_t, v[4 * i + 3] * p.out_t);
+            wq[8 + i] = e4m3x4(r0 * p.out_rs, r1 * p.out_rs, r2 * p.out_rs, r3 * p.out_rs);
+          }
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            __syncwarp();     // previous readers of the staging block are done
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 val = pl == 0 ? make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3])
+                                        : make_uint4(wq[4 * q], wq[4 * q + 1], wq[4 * q + 2], wq[4 * q + 3]);
+              stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = val;
+            }
+            __syncwarp();
+            if (c0 < p.Cout && !CTPN_DBG(p, 8)) {
+              // plane 0: 64 contiguous bytes per pixel (32 fp16).  plane 1: the pixel's 128-byte block of channel block
+              // c0 / 64 holds values at +0 and residuals at +64; this chunk owns 32 bytes of each
+              uint8_t *obase = reinterpret_cast<uint8_t *>(p.out) + (long long)pl * p.out_plane_stride * 2;
+              const int j = lane & 3;
+              const long long off = pl == 0 ? (long long)c0 * 2 + j * 16
+                                            : (long long)(c0 >> 6) * 128 + (c0 & 63) + (j >> 1) * 64 + (j & 1) * 16;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int pp = it * 8 + (lane >> 2);
+                const uint4 val = stage_w[pp * 4 + (j ^ ((pp >> 1) & 3))];
+                if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout * 2 + off) = val;
+              }
+            }
+          }
+        } else if (!out_f32) {
           uint32_t w[P][16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -446,7 +506,7 @@ static int cached_tmap(int dev, CUtensorMap *out, const void *ptr, int rank, con
   return CTPN_OK;
 }
 
-template <int BN, int P, int TAPS, int MC>
+template <int BN, int P, int TAPS, int MC, int F8 = 0>
 static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
   const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
   const size_t budget = 227 * 1024 - 1024 - kCtrlBytes - kStageBytes;
@@ -461,7 +521,7 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
   p.stages_a = sa;
   p.stages_b = sb;
   const size_t smem = 1024 + sa * a_stage + sb * b_stage + kStageBytes + kCtrlBytes;   // a constant of the instantiation
-  auto kernel = conv_tc_kernel<BN, P, TAPS, MC>;
+  auto kernel = conv_tc_kernel<BN, P, TAPS, MC, F8>;
   static bool attr_set[kMaxDevices];
   static int max_clusters[kMaxDevices];     // co-resident 2-CTA clusters of this instantiation (one CTA per SM)
   cudaLaunchConfig_t cfg = {};
@@ -488,7 +548,7 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
     }
   }
   char label[128];
-  if (prof_enabled()) snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d p%d bn%d%s", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, p.planes, BN, MC ? " mc" : "");
+  if (prof_enabled()) snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d %s%d bn%d%s", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, F8 ? "f16f8 p" : "p", p.planes, BN, MC ? " mc" : "");
   ProfScope prof(label, 2.0 * p.B * p.H * p.W * (double)p.taps * p.Cin * p.Cout, st);
   if (MC) cfg.gridDim = dim3(2 * std::min(max_clusters[dev], p.total_units));
   else cfg.gridDim = dim3(std::min(p.total_units, g_sms[dev]));
@@ -501,8 +561,12 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
 
 using namespace ctpn;
 
-extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B, int H,
-                            int W, int cin, int cout, int taps, int planes, int flags, void *stream) {
+namespace ctpn {
+struct QuantScales { float inv_main, inv_cross, out_s, out_t; };
+
+static int conv_tc_run(const void *in_planes, const void *w_planes, const float *bias, void *out, int B, int H, int W, int cin,
+                       int cout, int taps, int planes, int flags, const QuantScales *q, void *stream) {
+  const bool f8 = q != nullptr;
   CTPN_REQUIRE(in_planes && w_planes && bias && out, "ctpn_conv3x3: null pointer");
   CTPN_REQUIRE(taps == 9 || taps == 1, "ctpn_conv3x3: taps must be 9 or 1 (got %d)", taps);
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_conv3x3: planes must be 1..3 (got %d)", planes);
@@ -543,13 +607,18 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   p.out = out;
   p.out_plane_stride = (long long)B * p.Ho * p.Wo * cout;
   p.cout_pad = cout;
+  if (f8) {
+    CTPN_REQUIRE(q->inv_main > 0.f && q->inv_cross > 0.f && q->out_s > 0.f && q->out_t > 0.f, "ctpn_conv3x3_f16f8: scales must be positive");
+    p.inv_main = q->inv_main; p.inv_cross = q->inv_cross; p.out_s = q->out_s; p.out_t = q->out_t;
+    p.out_rs = kResidualGain * q->out_t / q->out_s;
+  }
   p.debug = tuning().debug;
 
   // N tile: 256 halves the A traffic per MAC but, with two accumulators per tile (P > 1), leaves no TMEM for
   // double buffering -- worth it only when the K loop is long enough to amortise the serialised epilogue.
   int BN = tuning().bn > 0 ? tuning().bn : (planes == 1 ? 256 : 128);
   if (!(BN == 64 || BN == 128 || BN == 256)) BN = 256;
-  if (planes > 1 && BN > 128) BN = 128;   // main + cross accumulators, double buffered: 4 * BN TMEM columns <= 512
+  if (planes > 1 && BN > 128) BN = 128;   // main + cross accumulators, double buffered: 4 * BN TMEM columns <= 512 (F16F8 too)
   while (BN > cout || cout % BN) BN >>= 1;
   p.tiles_n = cout / BN;
   p.nbuf = ((planes > 1 ? 2 : 1) * BN * 2 <= 512) ? 2 : 1;   // 512 TMEM columns per SM
@@ -581,6 +650,16 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
   if (BN == BN_ && planes == P_ && taps == T_) return launch_bn<BN_, P_, T_, 0>(dev, ta, tb, p, st)
 #define CTPN_TC_CASE_MC(BN_, P_) \
   if (mc && BN == BN_ && planes == P_) return launch_bn<BN_, P_, 9, 1>(dev, ta, tb, p, st)
+  if (f8) {
+    if (mc && BN == 128) return launch_bn<128, 2, 9, 1, 1>(dev, ta, tb, p, st);
+    if (mc && BN == 64) return launch_bn<64, 2, 9, 1, 1>(dev, ta, tb, p, st);
+    if (taps == 9 && BN == 128) return launch_bn<128, 2, 9, 0, 1>(dev, ta, tb, p, st);
+    if (taps == 9 && BN == 64) return launch_bn<64, 2, 9, 0, 1>(dev, ta, tb, p, st);
+    if (taps == 1 && BN == 128) return launch_bn<128, 2, 1, 0, 1>(dev, ta, tb, p, st);
+    if (taps == 1 && BN == 64) return launch_bn<64, 2, 1, 0, 1>(dev, ta, tb, p, st);
+    set_error("ctpn_conv3x3_f16f8: no kernel for BN=%d taps=%d", BN, taps);
+    return CTPN_ERR_INVALID;
+  }
   CTPN_TC_CASE_MC(256, 1); CTPN_TC_CASE_MC(128, 1); CTPN_TC_CASE_MC(64, 1);
   CTPN_TC_CASE_MC(256, 2); CTPN_TC_CASE_MC(128, 2); CTPN_TC_CASE_MC(64, 2);
   CTPN_TC_CASE_MC(128, 3); CTPN_TC_CASE_MC(64, 3);
@@ -594,4 +673,18 @@ extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const f
 #undef CTPN_TC_CASE
   set_error("ctpn_conv3x3: no kernel for BN=%d planes=%d taps=%d", BN, planes, taps);
   return CTPN_ERR_INVALID;
+}
+}  // namespace ctpn
+
+extern "C" int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B, int H,
+                            int W, int cin, int cout, int taps, int planes, int flags, void *stream) {
+  CTPN_REQUIRE(!(flags & CTPN_F_OUT_BF16X2), "ctpn_conv3x3: CTPN_F_OUT_BF16X2 is a flag of ctpn_conv3x3_f16f8");
+  return conv_tc_run(in_planes, w_planes, bias, out, B, H, W, cin, cout, taps, planes, flags, nullptr, stream);
+}
+
+extern "C" int ctpn_conv3x3_f16f8(const void *in_planes, const void *w_planes, const float *bias, void *out, int B, int H,
+                                  int W, int cin, int cout, int taps, int flags, float inv_main, float inv_cross, float out_s,
+                                  float out_t, void *stream) {
+  const QuantScales q{inv_main, inv_cross, out_s, out_t};
+  return conv_tc_run(in_planes, w_planes, bias, out, B, H, W, cin, cout, taps, 2, flags, &q, stream);
 }

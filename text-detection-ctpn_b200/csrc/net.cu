@@ -8,6 +8,10 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp8.h>
+
+#include <cmath>
+
 #include "common.cuh"
 #ifdef CTPN_DEBUG
 #include "testing/ctpn_b200_testing.h"
@@ -26,7 +30,7 @@ static const char *kFw = "lstm_o/bidirectional_rnn/fw/lstm_cell";
 static const char *kBw = "lstm_o/bidirectional_rnn/bw/lstm_cell";
 static const double kPixelMeans[3] = {102.9801, 115.9465, 122.7717};   // lib/fast_rcnn/config.py:200 (BGR)
 
-struct Tap { const void *ptr; long long pixels; int channels; bool planes; };
+struct Tap { const void *ptr; long long pixels; int channels; bool planes; float q_s = 0.f, q_t = 0.f; };   // q_s > 0: F16F8 planes
 
 }  // namespace ctpn
 
@@ -34,6 +38,12 @@ using namespace ctpn;
 
 struct ctpn_net {
   int planes = 2;
+  // F16F8 arithmetic for the 3x3 layers (planes = CTPN_ARITH_F16F8 at creation; common.cuh).  The matmuls around the
+  // BiLSTM (0.9 % of the FLOPs) stay on two bf16 planes.  Per-layer power-of-two scales: w_s / w_t from max|w| at
+  // finalize time; act_s / act_t (quantisation of the layer's OUTPUT) from the first batch seen (calibrate()).
+  bool f16f8 = false, calibrated = false;
+  float w_s[14] = {0}, w_t[14] = {0}, act_s[14] = {0}, act_t[14] = {0}, act_max[14] = {0};
+  unsigned *absmax_dev = nullptr;
   int conv_simt = 0, conv1_simt = 0, keep = 0;
   std::map<std::string, std::vector<float>> host;
   bool dirty = true;
@@ -74,9 +84,29 @@ static int upload_packed(ctpn_net *n, void **dst, const float *src, int taps, in
   return rc;
 }
 
+// upload a TF-layout [9][cin][cout] float32 kernel in the F16F8 weight format with scales from max|w|
+static int upload_packed_f16f8(ctpn_net *n, void **dst, const float *src, int cin, int cout, float *s_w, float *t_w) {
+  const size_t cnt = (size_t)9 * cin * cout;
+  float mx = 0.f;
+  for (size_t i = 0; i < cnt; ++i) mx = std::max(mx, fabsf(src[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) { set_error("weights are all zero or not finite"); return CTPN_ERR_INVALID; }
+  *s_w = exp2f(floorf(log2f(16384.f / mx)));      // fp16(w s_w) stays below 2^15
+  *t_w = exp2f(floorf(log2f(448.f / mx)));        // e4m3(w t_w) uses the top binade
+  float *tmp = nullptr;
+  CTPN_CUDA(cudaMalloc(&tmp, cnt * sizeof(float)));
+  cudaError_t e = cudaMemcpy(tmp, src, cnt * sizeof(float), cudaMemcpyHostToDevice);
+  int rc = e == cudaSuccess ? dev_alloc(n, dst, (size_t)2 * cout * 9 * cin * 2) : cuda_fail(e, "memcpy", __FILE__, __LINE__);
+  if (!rc) rc = ctpn_pack_weights_f16f8(tmp, 9, cin, cout, cout, *s_w, *t_w, *dst, nullptr);
+  if (!rc) { e = cudaDeviceSynchronize(); if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__); }
+  cudaFree(tmp);
+  return rc;
+}
+
 static void free_device(ctpn_net *n) {
   for (void *p : n->owned) cudaFree(p);
   n->owned.clear();
+  n->absmax_dev = nullptr;
+  n->calibrated = false;
 }
 
 static const std::vector<float> *need(ctpn_net *n, const std::string &name, size_t count) {
@@ -109,7 +139,9 @@ static int finalize(ctpn_net *n) {
       if ((rc = upload(n, &n->c11_w, w->data(), w->size()))) return rc;
       if ((rc = upload(n, &n->c11_b, b->data(), b->size()))) return rc;
     } else {
-      if ((rc = upload_packed(n, &n->conv_w[l], w->data(), 9, s.cin, s.cout, s.cout))) return rc;
+      if (n->f16f8) rc = upload_packed_f16f8(n, &n->conv_w[l], w->data(), s.cin, s.cout, &n->w_s[l], &n->w_t[l]);
+      else rc = upload_packed(n, &n->conv_w[l], w->data(), 9, s.cin, s.cout, s.cout);
+      if (rc) return rc;
       if ((rc = upload(n, &n->conv_b[l], b->data(), b->size()))) return rc;
     }
   }
@@ -149,6 +181,7 @@ static int finalize(ctpn_net *n) {
     if ((rc = upload_packed(n, &n->head_w, w.data(), 1, 512, 64, 64))) return rc;
     if ((rc = upload(n, &n->head_b, b.data(), b.size()))) return rc;
   }
+  if (n->f16f8 && (rc = dev_alloc(n, (void **)&n->absmax_dev, sizeof(unsigned)))) return rc;
   n->dirty = false;
   return CTPN_OK;
 }
@@ -200,6 +233,19 @@ __global__ void split_heads_kernel(const float *__restrict__ heads, long long M,
   else if (c < 60) cls[m * 20 + (c - 40)] = v;
 }
 
+// F16F8 planes -> float32: (h + residual / (2^11 t / s)) / s
+__global__ void f16f8_to_f32_kernel(const __half *__restrict__ hi, const uint8_t *__restrict__ cross, long long n, int C, float s, float t,
+                                    float *__restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long pix = i / C;
+  const int c = (int)(i % C);
+  const uint8_t rb = cross[pix * 2 * C + (c >> 6) * 128 + 64 + (c & 63)];
+  const __half_raw hr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)rb, __NV_E4M3);
+  const float r = __half2float(__half(hr)) / (kResidualGain * t / s);
+  dst[i] = (__half2float(hi[i]) + r) / s;
+}
+
 __global__ void planes_to_f32_kernel(const __nv_bfloat16 *__restrict__ src, long long n, long long plane_stride, int planes,
                                      float *__restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,13 +256,79 @@ __global__ void planes_to_f32_kernel(const __nv_bfloat16 *__restrict__ src, long
   dst[i] = v;
 }
 
+// max |x| over an fp16 tensor (non-negative floats order like their bit patterns; Inf / NaN come out on top)
+__global__ void absmax_f16_kernel(const __half *__restrict__ x, long long n, unsigned *__restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__half2float(x[i])));
+  unsigned bits = __float_as_uint(m);
+  if (m != m) bits = 0x7fc00000u;
+  for (int o = 16; o; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, bits);
+}
+
+// one 3x3 layer (or conv1_1 for l = 0) in the F16F8 arithmetic with the scales currently in the net
+static int run_layer_f16f8(ctpn_net *n, int l, const void *in, void *out, int B, int h, int w, void *stream) {
+  const ConvSpec &s = kConvs[l];
+  if (l == 0) return ctpn_conv1_1_tc_f16f8(in, 0, n->lut, n->c11_w, n->c11_b, out, B, h, w, n->act_s[0], n->act_t[0], stream);
+  const int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0) | (l == 13 ? CTPN_F_OUT_BF16X2 : 0);   // rpn_conv feeds the bf16x2 matmuls
+  const float inv_main = 1.f / (n->act_s[l - 1] * n->w_s[l]), inv_cross = 1.f / (kResidualGain * n->act_t[l - 1] * n->w_t[l]);
+  return ctpn_conv3x3_f16f8(in, n->conv_w[l], n->conv_b[l], out, B, h, w, s.cin, s.cout, 9, flags, inv_main, inv_cross,
+                            l == 13 ? 1.f : n->act_s[l], l == 13 ? 1.f : n->act_t[l], stream);
+}
+
+// Activation scales from data: every layer is run with provisional scales, the maximum of its fp16 plane is read back,
+// the scales are fixed (fp16 plane below 2^14, e4m3 copy two binades below saturation) and the layer is run again so the
+// next one sees its final input.  Synchronises per layer; happens once (first forward, or after "recalibrate").
+static int calibrate_f16f8(ctpn_net *n, const void *images, int src_is_f32, int B, int H, int W, const NetLayout &L, char *ws, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int h = H, w = W;
+  for (int l = 0; l < 13; ++l) {
+    const void *in = l == 0 ? images : (const void *)(ws + L.act[l - 1]);
+    float s_try = 1.f;
+    for (int attempt = 0; ; ++attempt) {
+      n->act_s[l] = s_try; n->act_t[l] = 1.f;
+      int rc = l == 0 ? ctpn_conv1_1_tc_f16f8(images, src_is_f32, n->lut, n->c11_w, n->c11_b, ws + L.act[0], B, h, w, s_try, 1.f, stream)
+                      : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, stream);
+      if (rc) return rc;
+      const long long cnt = (long long)B * L.h[l] * L.w[l] * kConvs[l].cout;
+      CTPN_CUDA(cudaMemsetAsync(n->absmax_dev, 0, sizeof(unsigned), st));
+      absmax_f16_kernel<<<1184, 256, 0, st>>>((const __half *)(ws + L.act[l]), cnt, n->absmax_dev);
+      CTPN_LAUNCH_CHECK();
+      unsigned bits = 0;
+      CTPN_CUDA(cudaMemcpyAsync(&bits, n->absmax_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      CTPN_CUDA(cudaStreamSynchronize(st));
+      float mx;
+      memcpy(&mx, &bits, sizeof(float));
+      CTPN_REQUIRE(mx == mx, "calibration: layer %s produced NaN", kConvs[l].name);
+      if (std::isinf(mx) || mx >= 60000.f) {     // the fp16 plane saturated: shrink and retry
+        CTPN_REQUIRE(attempt < 6, "calibration: activations of %s exceed 65504 * 2^48", kConvs[l].name);
+        s_try *= 1.f / 256.f;
+        continue;
+      }
+      const float amax = std::max(mx / s_try, 1e-20f);           // max |activation| of this layer on the calibration batch
+      n->act_max[l] = amax;
+      n->act_s[l] = amax * s_try > 16384.f || s_try < 1.f ? exp2f(floorf(log2f(16384.f / amax))) : 1.f;
+      n->act_t[l] = exp2f(floorf(log2f(448.f / amax)) - 2.f);    // two binades of headroom; beyond that e4m3 saturates (cross term only)
+      break;
+    }
+    int rc = l == 0 ? ctpn_conv1_1_tc_f16f8(images, src_is_f32, n->lut, n->c11_w, n->c11_b, ws + L.act[0], B, h, w, n->act_s[0], n->act_t[0], stream)
+                    : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, stream);
+    if (rc) return rc;
+    h = L.h[l]; w = L.w[l];
+  }
+  n->calibrated = true;
+  return CTPN_OK;
+}
+
 }  // namespace ctpn
 
 extern "C" int ctpn_net_create(ctpn_net_t **net, int planes) {
   CTPN_REQUIRE(net, "ctpn_net_create: null pointer");
-  CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_net_create: planes must be 1..3 (got %d)", planes);
+  CTPN_REQUIRE((planes >= 1 && planes <= 3) || planes == CTPN_ARITH_F16F8, "ctpn_net_create: planes must be 1..3 or CTPN_ARITH_F16F8 (got %d)", planes);
   ctpn_net *n = new ctpn_net();
-  n->planes = planes;
+  n->f16f8 = planes == CTPN_ARITH_F16F8;
+  n->planes = n->f16f8 ? 2 : planes;
   *net = n;
   return CTPN_OK;
 }
@@ -231,6 +343,7 @@ extern "C" int ctpn_net_destroy(ctpn_net_t *net) {
 extern "C" int ctpn_net_set_option(ctpn_net_t *net, const char *key, int value) {
   CTPN_REQUIRE(net && key, "ctpn_net_set_option: null pointer");
   if (!strcmp(key, "keep_activations")) net->keep = value != 0;
+  else if (!strcmp(key, "recalibrate")) net->calibrated = false;
 #ifdef CTPN_DEBUG   // float32 SIMT reference kernels: test library only
   else if (!strcmp(key, "conv_simt")) net->conv_simt = value != 0;
   else if (!strcmp(key, "conv1_simt")) net->conv1_simt = value != 0;
@@ -273,6 +386,20 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
   char *ws = (char *)workspace;
   const int P = net->planes;
   net->taps.clear();
+  if (net->f16f8) {
+    // 2-unit arithmetic: conv1_1 and the thirteen 3x3 layers on F16F8 planes (calibrated on the first batch)
+    if (!net->calibrated && (rc = calibrate_f16f8(net, images, src_is_f32, B, H, W, L, ws, stream))) return rc;
+    int hh = H, ww = W;
+    if ((rc = ctpn_conv1_1_tc_f16f8(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, net->act_s[0], net->act_t[0], stream))) return rc;
+    net->taps["conv1_1"] = Tap{ws + L.act[0], (long long)B * H * W, 64, true, net->act_s[0], net->act_t[0]};
+    for (int l = 1; l < 14; ++l) {
+      if ((rc = run_layer_f16f8(net, l, ws + L.act[l - 1], ws + L.act[l], B, hh, ww, stream))) return rc;
+      hh = L.h[l]; ww = L.w[l];
+      const ConvSpec &s = kConvs[l];
+      net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] =
+          Tap{ws + L.act[l], (long long)B * hh * ww, s.cout, true, l == 13 ? 0.f : net->act_s[l], l == 13 ? 0.f : net->act_t[l]};
+    }
+  }
 #ifdef CTPN_DEBUG
   auto conv1 = (net->conv_simt || net->conv1_simt) ? ctpn_conv1_1 : ctpn_conv1_1_tc;
   auto conv3 = net->conv_simt ? ctpn_conv3x3_simt : ctpn_conv3x3;
@@ -280,6 +407,7 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
   auto conv1 = ctpn_conv1_1_tc;
   auto conv3 = ctpn_conv3x3;
 #endif
+  if (!net->f16f8) {
   if ((rc = conv1(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, P, stream))) return rc;
   net->taps["conv1_1"] = Tap{ws + L.act[0], (long long)B * H * W, 64, true};
   int h = H, w = W;
@@ -289,6 +417,7 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
     if ((rc = conv3(ws + L.act[l - 1], net->conv_w[l], net->conv_b[l], ws + L.act[l], B, h, w, s.cin, s.cout, 9, P, flags, stream))) return rc;
     h = L.h[l]; w = L.w[l];
     net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] = Tap{ws + L.act[l], (long long)B * h * w, s.cout, true};
+  }
   }
   const int M = B * L.fh * L.fw;
   auto gemm = conv3;
@@ -315,7 +444,11 @@ extern "C" int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_
   *count = (size_t)n;
   if (!out_f32) return CTPN_OK;
   CTPN_REQUIRE(capacity >= (size_t)n, "ctpn_net_debug_tap: buffer too small (%zu < %lld)", capacity, n);
-  if (t.planes) {
+  if (t.planes && t.q_s > 0.f) {
+    f16f8_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half *)t.ptr, (const uint8_t *)t.ptr + n * 2, n,
+                                                                                       t.channels, t.q_s, t.q_t, out_f32);
+    CTPN_LAUNCH_CHECK();
+  } else if (t.planes) {
     planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)t.ptr, n, n, net->planes, out_f32);
     CTPN_LAUNCH_CHECK();
   } else {

@@ -231,10 +231,6 @@ probe_mma_rate_pair_kernel(int n_mma, int alternate_acc) {
 // instruction for both kinds (128 rows x 32 B of A), so the comparison isolates the tensor-pipe rate.
 namespace ctpn {
 
-__host__ __device__ constexpr uint32_t umma_idesc_e4m3(int M, int N) {   // kind::f8f6f4: A = B = E4M3 (format code 0), D = f32
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 template <int BN, int PAIR, int MODE>
 __global__ void __launch_bounds__(128, 1)
 probe_mma_kind_kernel(int n_mma) {

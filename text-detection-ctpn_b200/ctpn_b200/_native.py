@@ -53,6 +53,9 @@ SIGNATURES = {
     "ctpn_proposals_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "ctpn_proposals": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p]),
     "ctpn_pack_weights": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "ctpn_pack_weights_f16f8": (_i, [_p, _i, _i, _i, _i, _f, _f, _p, _p]),
+    "ctpn_conv3x3_f16f8": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _p]),
+    "ctpn_conv1_1_tc_f16f8": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
     "ctpn_conv1_1_tc": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ctpn_conv3x3": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ctpn_bilstm_recurrent": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),

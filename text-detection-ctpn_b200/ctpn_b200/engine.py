@@ -7,9 +7,10 @@ compute is in libctpn_b200.so (see include/ctpn_b200.h).  One Engine == one GPU.
     scores, boxes = eng.detect(im)               # == lib.fast_rcnn.test.test_ctpn
     results = eng.detect_batch(uint8_batch)      # [B,H,W,3] -> list of (scores, boxes)
 
-`planes` selects the arithmetic of the tensor-core layers (see include/ctpn_b200.h):
-1 = bf16 operands, 2 = bf16x2 split (~16 mantissa bits), 3 = bf16x3 split (float32-equivalent
-products); accumulation is always float32.
+`planes` / `mode` select the arithmetic of the tensor-core layers (see include/ctpn_b200.h); accumulation is always
+float32:  1 / "bf16" = bf16 operands (1 unit per MAC);  2 / "bf16x2" = bf16x2 split, ~16 mantissa bits (3 units);
+3 / "bf16x3" = bf16x3 split, float32-equivalent products (6 units);  4 / "f16f8" = fp16 operands + e4m3 cross terms for the
+3x3 layers (2 units; float32-faithful to ~5e-4 on the head logits; activation scales calibrated on the first batch).
 """
 import ctypes as C
 
@@ -26,7 +27,11 @@ DEFAULT_CFG = dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THR
 
 
 class Engine:
-    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False, streams=1):
+    MODES = {"bf16": 1, "bf16x2": 2, "bf16x3": 3, "f16f8": 4}
+
+    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False, streams=1, mode=None):
+        if mode is not None:
+            planes = self.MODES[mode]
         if not torch.cuda.is_available():
             raise N.CtpnError("ctpn_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -109,6 +114,10 @@ class Engine:
         N.check(N.lib.ctpn_net_forward(self._net, N.ptr(images), int(is_f32), B, H, W, N.ptr(cls), N.ptr(bbox),
                                        N.ptr(ws), ws.numel(), N.stream_ptr()), "ctpn_net_forward")
         return cls, bbox
+
+    def recalibrate(self):
+        """F16F8 mode: derive the activation scales again from the next batch (they are frozen after the first one)."""
+        N.check(N.lib.ctpn_net_set_option(self._net, b"recalibrate", 1), "set_option")
 
     def tap(self, name):
         """Debug: float32 copy of a named activation of the last forward (keep_activations=True)."""
@@ -280,7 +289,13 @@ class Engine:
             src = self._stage_host(images, slot)
             key = (slot, tuple(src.shape), src.dtype)
             if key not in bufs:
-                bufs[key] = torch.empty(tuple(src.shape), dtype=src.dtype, device=self.device)
+                # A fresh block from the caching allocator may be memory that tensors of the compute stream have just
+                # released while their kernels are still running: writing it from the copy stream would race with them
+                # (seen as a corrupted first image of the second batch).  Allocate in the copy stream's pool and let the
+                # copy stream catch up with the compute stream once, at creation; the buffer then lives as long as the engine.
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_stream(main)
+                    bufs[key] = torch.empty(tuple(src.shape), dtype=src.dtype, device=self.device)
             dev = bufs[key]
             with torch.cuda.stream(copy_stream):
                 if computed[slot] is not None:
