@@ -168,6 +168,13 @@ int ctpn_resize_out_size(int sh, int sw, double fx, double fy, int *dh, int *dw)
 int ctpn_resize_linear_u8(const void *src, int B, int sh, int sw, int channels, double fx, double fy, void *dst, int dh,
                           int dw, void *stream);
 
+/* The float32 rescale of _get_image_blob (lib/fast_rcnn/test.py:7-31) fused with the mean subtraction: uint8 BGR
+ * [B][sh][sw][3] -> float32 blob [B][dh][dw][3] = cv2.resize(float32(im) - PIXEL_MEANS, fx, fy, INTER_LINEAR) as OpenCV's own
+ * float code computes it (bit-exact; opencv-python builds that dispatch to Intel IPP differ from that by up to ~1.4e-2 on 8-bit-range data).
+ * lut[256][3] = float32(double(v) - PIXEL_MEANS[c]) (device).  dst size from ctpn_resize_out_size. */
+int ctpn_image_blob_f32(const void *src_u8, const float *lut, int B, int sh, int sw, double fx, double fy, float *dst, int dh,
+                        int dw, void *stream);
+
 /* ---- text lines on the host (replaces lib/text_connector/detectors.py:19-49 and the connector classes) ----
  * TextDetector.detect in C++ on the CPU: score filter (> 0.7), score order, NMS 0.2, proposal graph
  * (text_proposal_graph_builder.py:6-78), chains (other.py:16-29), horizontal (oriented = 0,

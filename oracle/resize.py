@@ -87,6 +87,52 @@ def resize_linear_u8(src, fx, fy=None):
     return out[:, :, 0] if squeeze else out
 
 
+def _taps_f32(dn, sn, scale, drop_border_fraction):
+    d = np.arange(dn, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if drop_border_fraction:
+        lo = s < 0
+        f[lo] = 0
+        s[lo] = 0
+        hi = s >= sn - 1
+        f[hi] = 0
+        s[hi] = sn - 1
+    return np.clip(s, 0, sn - 1), np.clip(s + 1, 0, sn - 1), (np.float32(1.0) - f).astype(np.float32), f
+
+
+def resize_linear_f32(src, fx, fy=None):
+    """cv2.resize(src, None, None, fx=fx, fy=fy, interpolation=cv2.INTER_LINEAR) for float32 [H,W,C] images as OpenCV's OWN
+    code computes it (the second rescale of _get_image_blob, lib/fast_rcnn/test.py:17-25, runs on the float32
+    mean-subtracted image): float weights (1 - f, f), horizontal pass S[sx] * a0 + S[sx+1] * a1, vertical pass
+    R0 * b0 + R1 * b1, every product and sum rounded to float32; an exact 1/2 scale is routed to INTER_AREA,
+    (((s00 + s01) + s10) + s11) * 0.25.  Pinned against cv2 with cv2.ipp.setUseIPP(False) in tests/test_resize_cpu.py;
+    IPP-dispatching builds (the opencv-python wheel) differ from this by up to ~1.4e-2 on 8-bit-range data (1100-px-wide image;
+    the gap grows with the width)."""
+    fy = fx if fy is None else fy
+    src = np.asarray(src)
+    assert src.dtype == np.float32 and src.ndim == 3
+    sh, sw = src.shape[:2]
+    dh, dw = out_size(sh, sw, fx, fy)
+    if 1.0 / fx == 2.0 and 1.0 / fy == 2.0:
+        out = np.zeros((dh, dw, src.shape[2]), np.float32)
+        for dy in range(dh):
+            ys = [y for y in (2 * dy, 2 * dy + 1) if y < sh]
+            for dx in range(dw):
+                xs = [x for x in (2 * dx, 2 * dx + 1) if x < sw]
+                vals = [src[y, x] for y in ys for x in xs]
+                acc = vals[0].copy()
+                for v in vals[1:]:
+                    acc = (acc + v).astype(np.float32)
+                out[dy, dx] = acc * np.float32(0.25) if len(vals) == 4 else acc / np.float32(len(vals))
+        return out
+    sx, sx1, ax0, ax1 = _taps_f32(dw, sw, 1.0 / fx, True)
+    sy, sy1, ay0, ay1 = _taps_f32(dh, sh, 1.0 / fy, False)
+    rows = (src[:, sx] * ax0[None, :, None]).astype(np.float32) + (src[:, sx1] * ax1[None, :, None]).astype(np.float32)
+    return ((rows[sy] * ay0[:, None, None]).astype(np.float32) + (rows[sy1] * ay1[:, None, None]).astype(np.float32)).astype(np.float32)
+
+
 def resize_im_scale(h, w, scale=600, max_scale=1200):
     """The factor resize_im (ctpn/demo.py:21-25) applies: short side -> scale unless the long side would exceed max_scale."""
     f = float(scale) / min(h, w)

@@ -34,3 +34,29 @@ def test_resize_im_rule_and_anisotropic():
     for shape in ((301, 203), (300, 203), (301, 202)):               # exact 1/2 with odd borders: INTER_AREA branch
         im = rs.randint(0, 256, shape + (3,)).astype(np.uint8)
         np.testing.assert_array_equal(R.resize_linear_u8(im, 0.5), cv2.resize(im, None, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR))
+
+
+def test_float32_linear_matches_opencv_own_code_and_bounds_the_ipp_difference():
+    """The float32 rescale of _get_image_blob (lib/fast_rcnn/test.py:17-25).  opencv-python dispatches float32 INTER_LINEAR
+    to Intel IPP; with IPP switched off OpenCV runs its own resize.cpp code, which the restatement reproduces bit for bit.
+    The IPP result differs from that through its float32 coordinate arithmetic: the gap grows with the image width and reaches
+    ~1.4e-2 (on 8-bit-range data) for a 1100-px-wide image; asserted < 5e-2, i.e. 2e-4 of the pixel range."""
+    import cv2
+    from oracle.resize import resize_linear_f32
+    means = np.array([102.9801, 115.9465, 122.7717])
+    rs = np.random.RandomState(5)
+    was = cv2.ipp.useIPP()
+    try:
+        for (h, w, f) in [(600, 1100, 1000.0 / 1100), (37, 53, 0.73), (300, 750, 1000.0 / 750), (128, 300, 2.0), (50, 70, 1.37),
+                          (64, 64, 0.5), (65, 63, 0.5)]:
+            im = rs.randint(0, 256, (h, w, 3)).astype(np.float32)
+            im -= means
+            mine = resize_linear_f32(im, f)
+            cv2.ipp.setUseIPP(False)
+            own = cv2.resize(im, None, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR)
+            cv2.ipp.setUseIPP(True)
+            ipp = cv2.resize(im, None, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR)
+            np.testing.assert_array_equal(mine, own)
+            assert np.abs(ipp - own).max() < 5e-2
+    finally:
+        cv2.ipp.setUseIPP(was)

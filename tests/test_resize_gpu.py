@@ -57,3 +57,36 @@ def test_detect_resized_equals_host_resize_then_detect(engine):
         t = torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda")
         o = torch.zeros((1, 9, 9, 3), dtype=torch.uint8, device="cuda")     # cv2 would produce 12 x 12
         N.check(N.lib.ctpn_resize_linear_u8(N.ptr(t), 1, 8, 8, 3, 1.5, 1.5, N.ptr(o), 9, 9, N.stream_ptr()), "resize")
+
+
+@pytest.mark.parametrize("h,w,f", [(600, 1100, 1000.0 / 1100), (37, 53, 0.73), (300, 750, 1000.0 / 750), (128, 300, 2.0), (64, 64, 0.5), (65, 63, 0.5)])
+def test_image_blob_f32_bit_exact_with_the_oracle(h, w, f):
+    """ctpn_image_blob_f32 (mean subtraction + float32 INTER_LINEAR, the second rescale of _get_image_blob) == the numpy
+    restatement of OpenCV's own float code, which tests/test_resize_cpu.py pins against cv2 with IPP off."""
+    from ctpn_b200 import Engine
+    from oracle.resize import resize_linear_f32
+    eng = Engine(None)
+    rs = np.random.RandomState(h + w)
+    ims = rs.randint(0, 256, (2, h, w, 3)).astype(np.uint8)
+    got = eng.image_blob(ims, f).cpu().numpy()
+    for b in range(2):
+        im = ims[b].astype(np.float32)
+        im -= np.array([[[102.9801, 115.9465, 122.7717]]])
+        np.testing.assert_array_equal(got[b], resize_linear_f32(im, f))
+
+
+def test_detect_scaled_equals_host_blob_path():
+    """Engine.detect_scaled (rescale rule + blob on the device) == test_ctpn's host route fed with the same blob."""
+    from ctpn_b200 import Engine
+    from oracle import synth
+    from oracle.resize import resize_linear_f32
+    eng = Engine(synth.make_weights(0), planes=2)
+    im = synth.make_image(3, 300, 560)                        # short side 300 -> x2 would give 1120 > 1000: scale = 1000/560
+    scale = 1000.0 / 560
+    src = im.astype(np.float32)
+    src -= np.array([[[102.9801, 115.9465, 122.7717]]])
+    blob = resize_linear_f32(src, scale)[None]
+    want = eng.rois_batch(blob, np.array([[blob.shape[1], blob.shape[2], scale]], np.float32))[0]
+    scores, boxes = eng.detect_scaled(im[None])[0]
+    np.testing.assert_array_equal(scores, want[:, 0])
+    np.testing.assert_array_equal(boxes, want[:, 1:5] / np.float32(scale))

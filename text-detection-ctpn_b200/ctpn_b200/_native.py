@@ -48,6 +48,7 @@ SIGNATURES = {
     "ctpn_text_groups_host": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p]),
     "ctpn_resize_out_size": (_i, [_i, _i, C.c_double, C.c_double, _p, _p]),
     "ctpn_resize_linear_u8": (_i, [_p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _i, _i, _p]),
+    "ctpn_image_blob_f32": (_i, [_p, _p, _i, _i, _i, C.c_double, C.c_double, _p, _i, _i, _p]),
     "ctpn_nms_workspace_bytes": (_z, [_i, _i]),
     "ctpn_nms_sorted": (_i, [_p, _p, _i, _i, _f, _i, _p, _p, _p, _z, _p]),
     "ctpn_proposals_workspace_bytes": (_z, [_i, _i, _i, _i]),

@@ -426,6 +426,41 @@ class Engine:
                                             N.stream_ptr()), "ctpn_resize_linear_u8")
         return out
 
+    def image_blob(self, images, im_scale):
+        """_get_image_blob (lib/fast_rcnn/test.py:7-31) on the device for a same-shape uint8 BGR batch [B,H,W,3]: mean
+        subtraction (float32(double(v) - PIXEL_MEANS)) fused with the float32 cv2.resize by im_scale.  Returns a float32
+        device blob [B,dh,dw,3], bit-exact with OpenCV's own float INTER_LINEAR code (IPP-dispatching cv2 builds differ
+        from that by up to ~1e-2 on 8-bit-range data; see csrc/resize.cu)."""
+        t = images if torch.is_tensor(images) else torch.from_numpy(np.ascontiguousarray(images))
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+            raise ValueError("image_blob expects a uint8 [B,H,W,3] batch")
+        t = t.to(self.device, non_blocking=True).contiguous()
+        B, H, W, _ = t.shape
+        if getattr(self, "_lut", None) is None:
+            means = np.array([102.9801, 115.9465, 122.7717])              # cfg.PIXEL_MEANS (config.py:200), BGR
+            self._lut = torch.from_numpy((np.arange(256, dtype=np.float64)[:, None] - means[None, :]).astype(np.float32)).to(self.device)
+        dh, dw = C.c_int(0), C.c_int(0)
+        N.check(N.lib.ctpn_resize_out_size(H, W, float(im_scale), float(im_scale), C.byref(dh), C.byref(dw)), "ctpn_resize_out_size")
+        out = torch.empty((B, dh.value, dw.value, 3), dtype=torch.float32, device=self.device)
+        N.check(N.lib.ctpn_image_blob_f32(N.ptr(t), N.ptr(self._lut), B, H, W, float(im_scale), float(im_scale), N.ptr(out),
+                                          dh.value, dw.value, N.stream_ptr()), "ctpn_image_blob_f32")
+        return out
+
+    def detect_scaled(self, images):
+        """test_ctpn() for a same-shape uint8 batch with the reference's rescaling rule on the device: im_scale =
+        SCALES[0] / short side, capped so that the long side stays within MAX_SIZE (test.py:13-20); scale 1 takes the
+        uint8 fast path, anything else image_blob().  Returns [(scores, boxes)] with boxes divided by im_scale (test.py:54-57)."""
+        H, W = int(images.shape[1]), int(images.shape[2])
+        target, max_size = float(self.cfg["SCALES"][0]), float(self.cfg["MAX_SIZE"])
+        im_scale = target / min(H, W)
+        if np.round(im_scale * max(H, W)) > max_size:
+            im_scale = max_size / max(H, W)
+        if im_scale == 1.0:
+            return self.detect_batch(images, 1.0)
+        blob = self.image_blob(images, im_scale)
+        info = np.array([[blob.shape[1], blob.shape[2], im_scale]] * blob.shape[0], np.float32)
+        return [(r[:, 0], r[:, 1:5] / np.float32(im_scale)) for r in self.rois_batch(blob, info)]
+
     def detect_resized(self, images, scale=600, max_scale=1200):
         """The front half of ctpn() (demo.py:59-61) for a same-shape uint8 batch: resize_im on the device (short side
         -> scale, long side <= max_scale), then the detector.  Returns ([(scores, boxes)], f); boxes are in the resized
