@@ -175,6 +175,10 @@ int ctpn_resize_linear_u8(const void *src, int B, int sh, int sw, int channels, 
 int ctpn_image_blob_f32(const void *src_u8, const float *lut, int B, int sh, int sw, double fx, double fy, float *dst, int dh,
                         int dw, void *stream);
 
+/* CRC-32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the per-tensor checksum of TF checkpoint V2
+ * files, used by the weight importer (ctpn_b200/tf_import.py) to verify every tensor it loads. */
+uint32_t ctpn_crc32c_host(const void *data, size_t n, uint32_t crc);
+
 /* ---- text lines on the host (replaces lib/text_connector/detectors.py:19-49 and the connector classes) ----
  * TextDetector.detect in C++ on the CPU: score filter (> 0.7), score order, NMS 0.2, proposal graph
  * (text_proposal_graph_builder.py:6-78), chains (other.py:16-29), horizontal (oriented = 0,

@@ -70,11 +70,26 @@ def _match_rois(got, got_idx, want, want_idx):
     return len(common) / float(len(want_idx)), float(ds), float(db)
 
 
+def rows_matched(got, want, tol=1e-3):
+    """Fraction of the oracle's rows (score, x1, y1, x2, y2) for which the engine has a row within tol * max(1, |b|)."""
+    if not len(want):
+        return 1.0
+    hit = 0
+    for r in want:
+        hit += bool(len(got)) and bool((np.abs(got - r).max(axis=1) <= tol * max(1.0, float(np.abs(r).max()))).any())
+    return hit / float(len(want))
+
+
+# measured on B200 (profiles/r2_pytest_gpu.txt): head max|diff| cls / bbox vs the float32 oracle at 600x900:
+# bf16x2 3.3e-4 / 3.4e-5, bf16x3 2.2e-4 / 2.3e-5, f16f8 6.8e-4 / 8.4e-5; bounds = those with headroom, all inside 1e-3
+HEAD_BOUNDS = {2: (6e-4, 8e-5), 3: (4e-4, 6e-5), 4: (1e-3, 2e-4)}
+
+
 @pytest.mark.parametrize("planes", [2, 3, 4])
 def test_end_to_end_600x900_against_oracle(weights, planes):
     """BASELINE.json config 1/2 shape: one 600x900 image, full path.  Head tensors within 1e-3;
     proposals: bit-exact against the oracle when both start from the engine's head tensors, and
-    >= 98% identical rows (boxes/scores within 1e-3) against the all-CPU oracle path."""
+    >= 99.9% identical rows (scores within 1e-5, boxes within 2e-4 relative) against the all-CPU oracle path."""
     from ctpn_b200 import Engine
     eng = Engine(weights, planes=planes)
     im = synth.make_image(0)
@@ -85,7 +100,7 @@ def test_end_to_end_600x900_against_oracle(weights, planes):
     cls_h, bbox_h = cls.cpu().numpy(), bbox.cpu().numpy()
     d_cls, d_box = np.abs(cls_h - ref["rpn_cls_score"]).max(), np.abs(bbox_h - ref["rpn_bbox_pred"]).max()
     print("planes", planes, "head max|diff| vs float32 oracle: cls %.2e bbox %.2e" % (d_cls, d_box))
-    assert d_cls < 1e-3 and d_box < 1e-3
+    assert d_cls < HEAD_BOUNDS[planes][0] and d_box < HEAD_BOUNDS[planes][1]
     info = np.array([[600, 900, 1.0]], np.float32)
     rois, index, count = eng.proposals(cls, bbox, torch.from_numpy(info), cls_is_logit=True)
     n = int(count[0])
@@ -103,7 +118,8 @@ def test_end_to_end_600x900_against_oracle(weights, planes):
     want2, _, want2_idx = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info, return_index=True)
     frac, ds, db = _match_rois(got, got_idx, want2, want2_idx)
     print("planes", planes, "e2e overlap %.4f  dscore %.2e  dbox %.2e" % (frac, ds, db))
-    assert frac >= 0.98 and ds < 1e-3 and db < 1e-3, (frac, ds, db)
+    # measured: overlap 1.0000 in every mode, dscore <= 1.3e-6, dbox <= 4.4e-5 (relative)
+    assert frac >= 0.999 and ds < 1e-5 and db < 2e-4, (frac, ds, db)
 
 
 def test_reference_api_test_ctpn_and_text_detector(weights):
@@ -127,10 +143,10 @@ def test_reference_api_test_ctpn_and_text_detector(weights):
         want, _ = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info)
         assert scores.dtype == np.float32 and boxes.shape == (scores.shape[0], 4)
         assert (np.diff(scores) <= 0).all() and scores.shape[0] <= cfg.TEST.RPN_POST_NMS_TOP_N
-        assert abs(scores.shape[0] - want.shape[0]) <= 10
-        # the strongest proposals agree with the oracle within 1e-3 (they are far from any tie/NMS boundary)
-        k = 50
-        np.testing.assert_allclose(scores[:k], want[:k, 0], atol=1e-3)
+        # ALL rows: same count up to NMS decisions that sit within float noise of the threshold, every oracle row present
+        assert abs(scores.shape[0] - want.shape[0]) <= 2
+        got = np.hstack([scores[:, None], boxes * np.float32(scale)])
+        assert rows_matched(got, want) >= 0.995
         lines = TextDetector().detect(boxes, scores[:, np.newaxis], im.shape[:2])
         assert lines.ndim == 2 and lines.shape[1] == 9 and lines.dtype == np.float64
 
@@ -153,6 +169,43 @@ def test_batch_equals_singles_and_simt_cross_check(weights):
     run_check("net_simt", "--B", 3, "--H", 128, "--W", 192, "--planes", 2, "--tol", 5e-4, env=DBG)
 
 
+def test_bf16_mode_measured_deviation(weights):
+    """BASELINE.json configs[2] arithmetic (bf16 operands, planes=1) does NOT meet the 1e-3 bar; this pins what it does
+    deliver at 600x900 (measured on B200: head logits within 0.11, 94.8 % of the oracle's rows reproduced within 1e-3)."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, planes=1)
+    im = synth.make_image(7)
+    blob, _ = net_cpu.image_blob(im)
+    ref = net_cpu.forward(blob, weights)
+    info = np.array([[600, 900, 1.0]], np.float32)
+    want, _ = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info)
+    cls, bbox = eng.forward_heads(torch.from_numpy(im[None]).cuda())
+    d_cls = np.abs(cls.cpu().numpy() - ref["rpn_cls_score"]).max()
+    d_box = np.abs(bbox.cpu().numpy() - ref["rpn_bbox_pred"]).max()
+    frac = rows_matched(eng.rois_batch(im[None], info)[0], want)
+    print("bf16: head cls %.3e bbox %.3e, oracle rows matched %.3f" % (d_cls, d_box, frac))
+    assert d_cls < 0.25 and d_box < 0.05 and frac >= 0.90
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_f16f8_mode_head_error_over_several_images(weights, seed):
+    """The 2-unit arithmetic on more images than the one of test_end_to_end: every one must stay inside the 1e-3 contract on
+    the head tensors (measured 6.8e-4 .. 7.9e-4 on the logits, < 1e-4 on the regressions) with all oracle rows reproduced."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, mode="f16f8")
+    im = synth.make_image(seed)
+    blob, _ = net_cpu.image_blob(im)
+    ref = net_cpu.forward(blob, weights)
+    info = np.array([[600, 900, 1.0]], np.float32)
+    want, _ = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info)
+    cls, bbox = eng.forward_heads(torch.from_numpy(im[None]).cuda())
+    d_cls = np.abs(cls.cpu().numpy() - ref["rpn_cls_score"]).max()
+    d_box = np.abs(bbox.cpu().numpy() - ref["rpn_bbox_pred"]).max()
+    frac = rows_matched(eng.rois_batch(im[None], info)[0], want)
+    print("f16f8 seed %d: head cls %.3e bbox %.3e, oracle rows matched %.4f" % (seed, d_cls, d_box, frac))
+    assert d_cls < 1e-3 and d_box < 2e-4 and frac >= 0.995
+
+
 def test_config4_high_resolution_1200x1600(weights):
     """BASELINE.json configs[3]: 1200x1600 images (75x100 feature map, 75 000 anchors, 12 000 into NMS).
     Uses the engine API directly (the reference's test_ctpn would first shrink the image to 600x800 unless
@@ -168,13 +221,7 @@ def test_config4_high_resolution_1200x1600(weights):
     want, _ = postproc.proposal_layer(ref["rpn_cls_prob_reshape"], ref["rpn_bbox_pred"], info[:1])
     got = rois[0]
     assert got.shape[0] == 1000 and want.shape[0] == 1000
-    k = 100                                                   # strongest proposals: far from sort/NMS decision boundaries
-    np.testing.assert_allclose(got[:k, 0], want[:k, 0], atol=1e-3)
-    found = 0
-    for r in want[:k]:
-        d = np.abs(got[:, 1:] - r[1:]).max(axis=1)
-        found += bool((d <= 1e-3 * np.maximum(1.0, np.abs(r[1:]).max())).any())
-    assert found >= 0.97 * k, found
+    assert rows_matched(got, want) >= 0.995                  # all 1000 rows, not only the strongest
 
 
 def test_config5_mixed_shapes_oriented_connector(weights):

@@ -79,6 +79,23 @@ def test_checkpoint_corruption_is_detected(tmp_path):
         T.read_checkpoint(prefix, verify=False)                             # truncated shard
 
 
+def test_large_tensor_corruption_is_detected(tmp_path):
+    """Every tensor is checksummed (conv / LSTM weights are far above the old 64 KB limit): one flipped bit in
+    the middle of a 9.4 MB conv kernel must not load."""
+    w = {"conv4_2/weights": np.random.RandomState(0).standard_normal((3, 3, 512, 512)).astype(np.float32), "b": np.ones(5, np.float32)}
+    prefix = str(tmp_path / "big.ckpt")
+    W.write_checkpoint(prefix, w)
+    got = T.read_checkpoint(prefix)
+    np.testing.assert_array_equal(got["conv4_2/weights"], w["conv4_2/weights"])
+    path = prefix + ".data-00000-of-00001"
+    data = bytearray(open(path, "rb").read())
+    data[len(data) // 2] ^= 0x10
+    open(path, "wb").write(bytes(data))
+    with pytest.raises(T.TFFormatError, match="checksum"):
+        T.read_checkpoint(prefix)
+    assert T.crc32c_fast(b"123456789") == 0xE3069283
+
+
 def test_latest_checkpoint_state_file(tmp_path):
     assert T.latest_checkpoint(str(tmp_path)) is None
     (tmp_path / "checkpoint").write_text('model_checkpoint_path: "VGGnet_fast_rcnn_iter_50000.ckpt"\n'

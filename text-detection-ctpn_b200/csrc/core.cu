@@ -110,3 +110,36 @@ extern "C" int ctpn_device_ok(int device_id) {
   }
   return CTPN_OK;
 }
+
+// ---- CRC-32C (Castagnoli), slicing-by-8: per-tensor checksums of TF checkpoints (ctpn_b200/tf_import.py) -------------
+namespace ctpn {
+static uint32_t g_crc_tab[8][256];
+static std::once_flag g_crc_once;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xffu];
+}
+}  // namespace ctpn
+
+extern "C" uint32_t ctpn_crc32c_host(const void *data, size_t n, uint32_t crc) {
+  std::call_once(ctpn::g_crc_once, ctpn::crc_init);
+  const uint8_t *p = (const uint8_t *)data;
+  auto &T = ctpn::g_crc_tab;
+  crc = ~crc;
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    v ^= crc;
+    crc = T[7][v & 0xff] ^ T[6][(v >> 8) & 0xff] ^ T[5][(v >> 16) & 0xff] ^ T[4][(v >> 24) & 0xff] ^ T[3][(v >> 32) & 0xff] ^
+          T[2][(v >> 40) & 0xff] ^ T[1][(v >> 48) & 0xff] ^ T[0][v >> 56];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = T[0][(crc ^ *p++) & 0xff] ^ (crc >> 8);
+  return ~crc;
+}

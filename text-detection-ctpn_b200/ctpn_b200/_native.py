@@ -42,6 +42,7 @@ SIGNATURES = {
     "ctpn_device_ok": (_i, [_i]),
     "ctpn_prof_enable": (_i, [_i]),
     "ctpn_prof_report": (_i, [_p, _z, C.POINTER(_z)]),
+    "ctpn_crc32c_host": (C.c_uint32, [_p, _z, C.c_uint32]),
     "ctpn_nms_host": (_i, [_p, _p, _p, _i, _i, _f, _i]),
     "ctpn_text_lines_host": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "ctpn_text_filter_nms_host": (_i, [_p, _p, _i, _p, _p, _p]),

@@ -22,6 +22,9 @@ def _proposal_engine():
 def proposal_layer(rpn_cls_prob_reshape, rpn_bbox_pred, im_info, cfg_key, _feat_stride=[16, ], anchor_scales=[16, ]):
     if isinstance(cfg_key, bytes):
         cfg_key = cfg_key.decode('ascii')
+    if cfg_key != 'TEST':
+        # the training graph (anchor targets, losses) is out of scope of this inference engine
+        raise NotImplementedError("proposal_layer: only cfg_key='TEST' is supported (got %r)" % (cfg_key,))
     cls_prob = np.ascontiguousarray(rpn_cls_prob_reshape, np.float32)
     bbox = np.ascontiguousarray(rpn_bbox_pred, np.float32)
     assert cls_prob.shape[0] == 1, 'Only single item batches are supported'

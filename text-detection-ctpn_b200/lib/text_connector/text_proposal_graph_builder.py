@@ -4,7 +4,10 @@ per-proposal Python scans replaced by dense float32 array operations.  Semantics
     stop at the first bucket that holds any compatible box (:10-32);
   * compatibility = vertical overlap >= 0.7 and height similarity >= 0.7 in float32 (:40-54);
   * successor = best-scoring box of that bucket, first one on ties (:72);
-  * the edge is kept iff score[i] >= max score of the successor's nearest precursors (:34-38)."""
+  * the edge is kept iff score[i] >= max score of the successor's nearest precursors (:34-38).
+Comparisons against the python-float thresholds run in float32 (NumPy >= 2 weak-scalar promotion); the reference on
+NumPy 1.x compared float32 scalars in float64, which differs only when a ratio equals float32(0.7) exactly.  The goldens
+were generated under NumPy 2."""
 import numpy as np
 
 from .text_connect_cfg import Config as TextLineCfg
