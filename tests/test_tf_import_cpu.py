@@ -81,8 +81,8 @@ def test_checkpoint_corruption_is_detected(tmp_path):
 
 def test_large_tensor_corruption_is_detected(tmp_path):
     """Every tensor is checksummed (conv / LSTM weights are far above the old 64 KB limit): one flipped bit in
-    the middle of a 9.4 MB conv kernel must not load."""
-    w = {"conv4_2/weights": np.random.RandomState(0).standard_normal((3, 3, 512, 512)).astype(np.float32), "b": np.ones(5, np.float32)}
+    the middle of a 2.4 MB conv kernel must not load."""
+    w = {"conv4_2/weights": np.random.RandomState(0).standard_normal((3, 3, 256, 256)).astype(np.float32), "b": np.ones(5, np.float32)}
     prefix = str(tmp_path / "big.ckpt")
     W.write_checkpoint(prefix, w)
     got = T.read_checkpoint(prefix)

@@ -49,6 +49,27 @@ def crc32c_bitwise(data):
     return crc ^ 0xFFFFFFFF
 
 
+_TABLE = None
+
+
+def crc32c_table(data):
+    """Byte-wise table version of the same polynomial (for tensors too large for the bitwise loop); a real TF Saver stores
+    the checksum of EVERY tensor."""
+    global _TABLE
+    if _TABLE is None:
+        _TABLE = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ (0x82F63B78 & -(c & 1))
+            _TABLE.append(c)
+    crc = 0xFFFFFFFF
+    t = _TABLE
+    for byte in data:
+        crc = t[(crc ^ byte) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
 def masked(crc):
     return ((((crc >> 15) | (crc << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
 
@@ -135,8 +156,7 @@ def write_checkpoint(prefix, tensors, block_size=4096, compress=False, write_sta
         raw = a.astype(a.dtype.newbyteorder("<")).tobytes()
         entry = f_varint(1, DT[a.dtype]) + f_bytes(2, shape_proto(a.shape)) + f_varint(3, 0) + f_varint(4, len(data)) + \
             f_varint(5, len(raw))
-        if len(raw) <= (1 << 16):   # the bitwise crc is slow; big tensors go without (the reader checks small ones only)
-            entry += f_fixed32(6, masked(crc32c_bitwise(raw)))
+        entry += f_fixed32(6, masked(crc32c_bitwise(raw) if len(raw) <= (1 << 12) else crc32c_table(raw)))
         tb.add(name.encode("utf-8"), entry)
         data += raw
     with open(prefix + ".index", "wb") as f:
