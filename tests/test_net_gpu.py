@@ -151,6 +151,32 @@ def test_reference_api_test_ctpn_and_text_detector(weights):
         assert lines.ndim == 2 and lines.shape[1] == 9 and lines.dtype == np.float64
 
 
+def test_demo_pb_frozen_graph_path_equals_checkpoint_path(weights, tmp_path, monkeypatch):
+    """ctpn/demo_pb.py (demo_pb.py:55-98 of the reference): weights from a frozen GraphDef, head tensors fetched by graph name,
+    proposal_layer called directly, TextDetector, res file -- the same result file as ctpn/demo.py's ctpn() on that image."""
+    import cv2
+    import tf_format_writer as W
+    from ctpn import demo, demo_pb
+    from ctpn_b200 import Session
+    from lib.networks.factory import get_network
+    pb = str(tmp_path / "ctpn.pb")
+    W.write_frozen_graph(pb, weights)
+    im_path = str(tmp_path / "img_7.png")
+    cv2.imwrite(im_path, synth.make_image(70, 450, 640))
+    out_a, out_b = tmp_path / "a", tmp_path / "b"
+    out_a.mkdir(); out_b.mkdir()
+    sess = Session(planes=2)
+    sess.restore(pb)
+    with pytest.raises(KeyError):
+        sess.graph.get_tensor_by_name("conv5_3/Relu:0")
+    monkeypatch.setattr(demo, "RESULTS_DIR", str(out_a))
+    lines = demo_pb.detect_pb(sess, im_path)
+    assert lines.ndim == 2 and lines.shape[1] == 9
+    monkeypatch.setattr(demo, "RESULTS_DIR", str(out_b))
+    demo.ctpn(Session(weights, planes=2), get_network("VGGnet_test"), im_path)
+    assert open(out_a / "res_img_7.txt", "rb").read() == open(out_b / "res_img_7.txt", "rb").read()
+
+
 def test_batch_equals_singles_and_simt_cross_check(weights):
     from ctpn_b200 import Engine
     eng = Engine(weights, planes=2)

@@ -20,46 +20,58 @@ namespace cg = cooperative_groups;
 
 namespace ctpn {
 
-constexpr int kHid = 128, kGates = 512, kHalf = 64, kLocalCols = 256;
+constexpr int kHid = 128, kGates = 512;
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-template <int RG>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+// NC = CTAs per cluster (2 or 4): CTA `rank` owns hidden units [rank * 128/NC, (rank + 1) * 128/NC) and the 4 gate columns of
+// each.  NC = 4 halves the resident weight slice (64 KiB), so two CTAs fit on an SM: 16 warps per SM instead of 8 for this
+// latency-bound loop (launched as clusters through cudaLaunchKernelEx).
+template <int RG, int NC>
+__global__ void __launch_bounds__(256, NC == 4 ? 2 : 1)
 bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, const float *__restrict__ wh_bw,
               __nv_bfloat16 *__restrict__ out, int R, int W, int planes) {
+  constexpr int kUnits = kHid / NC;          // hidden units of this CTA
+  constexpr int kLocalCols = 4 * kUnits;     // their i, j, f, o gate columns
+  constexpr int kCG = kLocalCols / 4;        // column groups (4 adjacent columns per thread)
+  constexpr int kRGroups = 256 / kCG;        // row groups
   extern __shared__ __align__(16) float smem[];
-  float *Ws = smem;                          // [128][256]  recurrent weights of this CTA's 64 units
+  float *Ws = smem;                          // [128][kLocalCols]  recurrent weights of this CTA's units
   float *hbuf = Ws + kHid * kLocalCols;      // [2][RG][128] full hidden state, double buffered
   float *gates = hbuf + 2 * RG * kHid;       // [RG][256]    pre-activations of this CTA's columns
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int cid = blockIdx.x >> 1;                       // cluster index
+  static_assert(NC == 2 || NC == 4, "cluster of 2 or 4 CTAs");
+  const int cid = blockIdx.x / NC;                       // cluster index
   const int groups = (R + RG - 1) / RG;
   const int dir = cid / groups, row0 = (cid % groups) * RG;
   const int t = threadIdx.x;
   // mat-vec phase: thread = 4 adjacent local columns x RG/4 rows (register tile: 4 + RG/4 shared-memory loads
   // per 4 * RG/4 * 4 FMAs); cell phase: thread = unit ul, rows (t >> 6) + 4q
-  constexpr int RT = RG / 4;
-  const int cg = t & 63, rg = t >> 6;                    // column group (4 columns), row group (RT rows)
-  const int lc0 = cg * 4;                                // first local column; gate = lc0 >> 6, unit = lc0 & 63
-  const int gcol0 = (lc0 >> 6) * kHid + rank * kHalf + (lc0 & 63);   // column in the 512-wide gate vector
-  const int ul = t & 63;
+  constexpr int RT = RG / kRGroups;
+  static_assert(RT >= 1 && RT * kRGroups == RG, "RG must be a multiple of the row-group count");
+  const int cg = t % kCG, rg = t / kCG;                  // column group (4 columns), row group (RT rows)
+  const int lc0 = cg * 4;                                // first local column; gate = lc0 / kUnits, unit = lc0 % kUnits
+  const int gcol0 = (lc0 / kUnits) * kHid + rank * kUnits + (lc0 % kUnits);   // column in the 512-wide gate vector
+  const int ul = t % kUnits;
   const float *wh = dir ? wh_bw : wh_fw;
   // Shared-memory layout of the weights for packed (f32x2) FMAs: [column pair half][k pair][column group][4] with
   // the 4 floats = (col a: k even, k odd; col b: k even, k odd), so one LDS.128 hands a thread two (k, k+1) weight
   // pairs and consecutive lanes read consecutive 16-byte chunks (conflict-free).
   for (int i = t; i < kHid * kLocalCols; i += 256) {
-    const int k = i >> 8, lc = i & 255;
+    const int k = i / kLocalCols, lc = i % kLocalCols;
     const int cgi = lc >> 2, cc = lc & 3;
-    Ws[(((cc >> 1) * (kHid / 2) + (k >> 1)) * 64 + cgi) * 4 + (cc & 1) * 2 + (k & 1)] =
-        wh[k * kGates + (lc >> 6) * kHid + rank * kHalf + (lc & 63)];
+    Ws[(((cc >> 1) * (kHid / 2) + (k >> 1)) * kCG + cgi) * 4 + (cc & 1) * 2 + (k & 1)] =
+        wh[k * kGates + (lc / kUnits) * kHid + rank * kUnits + (lc % kUnits)];
   }
   for (int i = t; i < 2 * RG * kHid; i += 256) hbuf[i] = 0.f;
-  float *peer_h = cluster.map_shared_rank(hbuf, rank ^ 1);
-  float c_state[RG / 4];
+  float *peer_h[NC];
 #pragma unroll
-  for (int q = 0; q < RG / 4; ++q) c_state[q] = 0.f;
+  for (int r = 0; r < NC; ++r) peer_h[r] = cluster.map_shared_rank(hbuf, r);
+  constexpr int kCellRows = RG / (256 / kUnits);         // rows per thread in the cell phase
+  float c_state[kCellRows];
+#pragma unroll
+  for (int q = 0; q < kCellRows; ++q) c_state[q] = 0.f;
   cluster.sync();
 
   const long long plane_stride = (long long)R * W * 2 * kHid;
@@ -73,8 +85,7 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
   for (int step = 0; step < W; ++step) {
     const int tpos = dir ? W - 1 - step : step;
     const float *hc = hbuf + (step & 1) * RG * kHid;
-    float *hn = hbuf + ((step + 1) & 1) * RG * kHid;
-    float *hn_peer = peer_h + ((step + 1) & 1) * RG * kHid;
+    const int hn_off = ((step + 1) & 1) * RG * kHid;
     // acc[r][c] = (sum over even k, sum over odd k) for local column lc0 + c: one FFMA2 (sm_100 fma.rn.f32x2)
     // advances two k at once with the natural register pairs (h[k], h[k+1]) x (w[k][c], w[k+1][c]).
     float2 acc[RT][4];
@@ -93,11 +104,11 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
       }
     }
     const float4 *w_lo = reinterpret_cast<const float4 *>(Ws) + cg;                       // columns lc0, lc0 + 1
-    const float4 *w_hi = reinterpret_cast<const float4 *>(Ws) + (kHid / 2) * 64 + cg;     // columns lc0 + 2, lc0 + 3
+    const float4 *w_hi = reinterpret_cast<const float4 *>(Ws) + (kHid / 2) * kCG + cg;    // columns lc0 + 2, lc0 + 3
 #pragma unroll 2
     for (int k = 0; k < kHid; k += 4) {
-      const float4 wa0 = w_lo[(k >> 1) * 64], wa1 = w_lo[((k >> 1) + 1) * 64];
-      const float4 wb0 = w_hi[(k >> 1) * 64], wb1 = w_hi[((k >> 1) + 1) * 64];
+      const float4 wa0 = w_lo[(k >> 1) * kCG], wa1 = w_lo[((k >> 1) + 1) * kCG];
+      const float4 wb0 = w_hi[(k >> 1) * kCG], wb1 = w_hi[((k >> 1) + 1) * kCG];
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
         const float4 h4 = *reinterpret_cast<const float4 *>(hc + (rg * RT + r) * kHid + k);
@@ -117,18 +128,18 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
       *reinterpret_cast<float4 *>(gates + (rg * RT + r) * kLocalCols + lc0) =
           make_float4(acc[r][0].x + acc[r][0].y, acc[r][1].x + acc[r][1].y, acc[r][2].x + acc[r][2].y, acc[r][3].x + acc[r][3].y);
     __syncthreads();
-    // cell update: thread -> unit ul, rows (t>>6) + 4q
+    // cell update: thread -> unit ul, rows (t / kUnits) + (256 / kUnits) * q
 #pragma unroll
-    for (int q = 0; q < RG / 4; ++q) {
-      const int r = (t >> 6) + 4 * q;
-      const float gi = gates[r * kLocalCols + ul], gj = gates[r * kLocalCols + 64 + ul];
-      const float gf = gates[r * kLocalCols + 128 + ul], go = gates[r * kLocalCols + 192 + ul];
+    for (int q = 0; q < kCellRows; ++q) {
+      const int r = (t / kUnits) + (256 / kUnits) * q;
+      const float gi = gates[r * kLocalCols + ul], gj = gates[r * kLocalCols + kUnits + ul];
+      const float gf = gates[r * kLocalCols + 2 * kUnits + ul], go = gates[r * kLocalCols + 3 * kUnits + ul];
       const float c = sigmoidf_acc(gf + 1.0f) * c_state[q] + sigmoidf_acc(gi) * tanhf(gj);
       const float h = sigmoidf_acc(go) * tanhf(c);
       c_state[q] = c;
-      const int u = rank * kHalf + ul;
-      hn[r * kHid + u] = h;
-      hn_peer[r * kHid + u] = h;
+      const int u = rank * kUnits + ul;
+#pragma unroll
+      for (int pr = 0; pr < NC; ++pr) peer_h[pr][hn_off + r * kHid + u] = h;     // own copy and every peer's (DSMEM)
       const int row = row0 + r;
       if (row < R) {
         __nv_bfloat16 pl[3];
@@ -141,14 +152,26 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
   }
 }
 
-template <int RG>
+template <int RG, int NC>
 static int launch_bilstm(const float *xproj, const float *wh_fw, const float *wh_bw, void *out, int R, int W, int planes,
                          cudaStream_t st) {
+  constexpr int kLocalCols = 4 * kHid / NC;
   const size_t smem = (size_t)(kHid * kLocalCols + 2 * RG * kHid + RG * kLocalCols) * sizeof(float);
-  CTPN_CUDA(cudaFuncSetAttribute(bilstm_kernel<RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kernel = bilstm_kernel<RG, NC>;
+  CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups = (R + RG - 1) / RG;
   ProfScope prof("bilstm_recurrent", 2.0 * 2.0 * R * W * 128.0 * 512.0, st);
-  bilstm_kernel<RG><<<2 * 2 * groups, 256, smem, st>>>(xproj, wh_fw, wh_bw, (__nv_bfloat16 *)out, R, W, planes);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = NC; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.gridDim = dim3(NC * 2 * groups);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  CTPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, xproj, wh_fw, wh_bw, (__nv_bfloat16 *)out, R, W, planes));
   CTPN_LAUNCH_CHECK();
   return CTPN_OK;
 }
@@ -163,9 +186,16 @@ extern "C" int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, con
   CTPN_REQUIRE(R > 0 && W > 0, "ctpn_bilstm_recurrent: bad shape R=%d W=%d", R, W);
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_bilstm_recurrent: planes must be 1..3");
   cudaStream_t st = (cudaStream_t)stream;
-  // rows per cluster: as many as keeps every SM busy in a single wave (148 SMs = 74 clusters per direction pair)
-  if (R >= 32 * 37) return launch_bilstm<32>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
-  if (R >= 16 * 37) return launch_bilstm<16>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
-  if (R >= 8 * 37) return launch_bilstm<8>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
-  return launch_bilstm<4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  // rows per cluster: as many as keeps every SM busy in a single wave.  Large batches: 4-CTA clusters, two CTAs per SM
+  // (R = 1184: 74 clusters x 4 CTAs = 296 = 2 x 148); small ones: 2-CTA clusters of fewer rows each.
+#ifdef CTPN_DEBUG
+  static const int force_nc = [] { const char *e = getenv("CTPN_LSTM_NC"); return e ? atoi(e) : 0; }();
+#else
+  constexpr int force_nc = 0;
+#endif
+  if (R >= 32 * 37 && force_nc != 2) return launch_bilstm<32, 4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 32 * 37) return launch_bilstm<32, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 16 * 37) return launch_bilstm<16, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  if (R >= 8 * 37) return launch_bilstm<8, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
+  return launch_bilstm<4, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
 }

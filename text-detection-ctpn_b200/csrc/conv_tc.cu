@@ -63,6 +63,7 @@ struct ConvTcParams {
   // F16F8 arithmetic (common.cuh): value = main * inv_main + cross * inv_cross; outputs are re-quantised as
   // h = fp16(v * out_s), e4m3(v * out_t), e4m3((v * out_s - h) * out_rs) with out_rs = 2^11 * out_t / out_s
   float inv_main, inv_cross, out_s, out_t, out_rs;
+  int stage_small;          // 1: 512-byte staging block per epilogue warp (8 pixels per round) -- frees room for a 4th weight stage
 };
 
 constexpr int kTcThreads = 352;   // warps: 0 B-producer, 1 MMA, 2-5 epilogue set 0, 6 A-producer, 7-10 epilogue set 1
@@ -104,7 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t a_stage = (uint32_t)P * p.patch_bytes, b_stage = (uint32_t)P * kBBytes;
   const uint32_t ring_b = ring_a + (uint32_t)p.stages_a * a_stage;
   uint8_t *stage_buf = smem_raw + (ring_b - raw) + (size_t)p.stages_b * b_stage;   // epilogue store staging
-  uint8_t *ctrl = stage_buf + kStageBytes;
+  uint8_t *ctrl = stage_buf + (p.stage_small ? kStageBytes / 4 : kStageBytes);
   const uint32_t fullA = smem_u32(ctrl), emptyA = fullA + 8 * kMaxStages;
   const uint32_t fullB = emptyA + 8 * kMaxStages, emptyB = fullB + 8 * kMaxStages;
   const uint32_t tfull0 = emptyB + 8 * kMaxStages, tempty0 = tfull0 + 16;
@@ -314,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)(pix & 0xffffffffll), it * 8 + (lane >> 2));
         spix[it] = (hi << 32) | lo;
       }
-      uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + ewarp * 32 * kStagePitch);
+      uint4 *stage_w = reinterpret_cast<uint4 *>(stage_buf + ewarp * (p.stage_small ? 8 : 32) * kStagePitch);
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
@@ -359,7 +360,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], p.TW));
           }
         }
-        if (F8 && !out_f32 && !(p.flags & CTPN_F_OUT_BF16X2)) {
+        if (F8 && pool && !out_f32 && !(p.flags & CTPN_F_OUT_BF16X2)) {
+          // Pooled F16F8 output without staging: after the shuffles all four lanes of a 2x2 window (l, l^1, l^8, l^9) hold the
+          // pooled value, so each takes one quarter (8 channels) of the chunk: a quarter of the conversions, and the four
+          // lanes' stores form 64 contiguous bytes of the fp16 plane and 32 + 32 of the e4m3 plane (full sectors).
+          const int j = (lane & 1) | ((lane >> 2) & 2);
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = j == 0 ? v[k] : j == 1 ? v[8 + k] : j == 2 ? v[16 + k] : v[24 + k];
+          const bool okw = oy < p.Ho && ox < p.Wo;
+          float r[8];
+          uint4 hw;
+          hw.x = f16x2_split(x[0] * p.out_s, x[1] * p.out_s, r[0], r[1]);
+          hw.y = f16x2_split(x[2] * p.out_s, x[3] * p.out_s, r[2], r[3]);
+          hw.z = f16x2_split(x[4] * p.out_s, x[5] * p.out_s, r[4], r[5]);
+          hw.w = f16x2_split(x[6] * p.out_s, x[7] * p.out_s, r[6], r[7]);
+          const uint2 qv = make_uint2(e4m3x4(x[0] * p.out_t, x[1] * p.out_t, x[2] * p.out_t, x[3] * p.out_t),
+                                      e4m3x4(x[4] * p.out_t, x[5] * p.out_t, x[6] * p.out_t, x[7] * p.out_t));
+          const uint2 qr = make_uint2(e4m3x4(r[0] * p.out_rs, r[1] * p.out_rs, r[2] * p.out_rs, r[3] * p.out_rs),
+                                      e4m3x4(r[4] * p.out_rs, r[5] * p.out_rs, r[6] * p.out_rs, r[7] * p.out_rs));
+          if (okw && c0 < p.Cout && !CTPN_DBG(p, 8)) {
+            uint8_t *o0 = reinterpret_cast<uint8_t *>(p.out) + pix * p.Cout * 2;
+            uint8_t *o1 = o0 + p.out_plane_stride * 2 + (long long)(c0 >> 6) * 128 + (c0 & 63) + j * 8;
+            *reinterpret_cast<uint4 *>(o0 + (long long)c0 * 2 + j * 16) = hw;
+            *reinterpret_cast<uint2 *>(o1) = qv;
+            *reinterpret_cast<uint2 *>(o1 + 64) = qr;
+          }
+        } else if (F8 && !out_f32 && !(p.flags & CTPN_F_OUT_BF16X2)) {
           // F16F8 planes: fp16 words, then the e4m3 copies of the values and of the residuals (8 + 8 words)
           uint32_t wh[16], wq[16];
 #pragma unroll
@@ -370,28 +397,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             wq[i] = e4m3x4(v[4 * i] * p.out_t, v[4 * i + 1] * p.out_t, v[4 * i + 2] * p.out_t, v[4 * i + 3] * p.out_t);
             wq[8 + i] = e4m3x4(r0 * p.out_rs, r1 * p.out_rs, r2 * p.out_rs, r3 * p.out_rs);
           }
+          const int j = lane & 3;
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) {
-            __syncwarp();     // previous readers of the staging block are done
+            // plane 0: 64 contiguous bytes per pixel (32 fp16).  plane 1: the pixel's 128-byte block of channel block
+            // c0 / 64 holds values at +0 and residuals at +64; this chunk owns 32 bytes of each
+            uint8_t *obase = reinterpret_cast<uint8_t *>(p.out) + (long long)pl * p.out_plane_stride * 2;
+            const long long off = pl == 0 ? (long long)c0 * 2 + j * 16
+                                          : (long long)(c0 >> 6) * 128 + (c0 & 63) + (j >> 1) * 64 + (j & 1) * 16;
+            const bool st_ok = c0 < p.Cout && !CTPN_DBG(p, 8);
+            if (!p.stage_small) {
+              __syncwarp();     // previous readers of the staging block are done
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 val = pl == 0 ? make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3])
-                                        : make_uint4(wq[4 * q], wq[4 * q + 1], wq[4 * q + 2], wq[4 * q + 3]);
-              stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = val;
-            }
-            __syncwarp();
-            if (c0 < p.Cout && !CTPN_DBG(p, 8)) {
-              // plane 0: 64 contiguous bytes per pixel (32 fp16).  plane 1: the pixel's 128-byte block of channel block
-              // c0 / 64 holds values at +0 and residuals at +64; this chunk owns 32 bytes of each
-              uint8_t *obase = reinterpret_cast<uint8_t *>(p.out) + (long long)pl * p.out_plane_stride * 2;
-              const int j = lane & 3;
-              const long long off = pl == 0 ? (long long)c0 * 2 + j * 16
-                                            : (long long)(c0 >> 6) * 128 + (c0 & 63) + (j >> 1) * 64 + (j & 1) * 16;
+              for (int q = 0; q < 4; ++q) {
+                const uint4 val = pl == 0 ? make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3])
+                                          : make_uint4(wq[4 * q], wq[4 * q + 1], wq[4 * q + 2], wq[4 * q + 3]);
+                stage_w[lane * 4 + (q ^ ((lane >> 1) & 3))] = val;
+              }
+              __syncwarp();
+              if (st_ok) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  const int pp = it * 8 + (lane >> 2);
+                  const uint4 val = stage_w[pp * 4 + (j ^ ((pp >> 1) & 3))];
+                  if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout * 2 + off) = val;
+                }
+              }
+            } else {
+              // 8 pixels per round through a 512-byte block: lanes 8 it .. 8 it + 7 deposit their 64 bytes, all 32 lanes
+              // then store one 16-byte piece each (4 lanes = one pixel's 64 contiguous bytes)
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
-                const int pp = it * 8 + (lane >> 2);
-                const uint4 val = stage_w[pp * 4 + (j ^ ((pp >> 1) & 3))];
-                if ((okmask >> pp) & 1u) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout * 2 + off) = val;
+                __syncwarp();
+                if ((lane >> 3) == it) {
+                  const int row = lane & 7;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const uint4 val = pl == 0 ? make_uint4(wh[4 * q], wh[4 * q + 1], wh[4 * q + 2], wh[4 * q + 3])
+                                              : make_uint4(wq[4 * q], wq[4 * q + 1], wq[4 * q + 2], wq[4 * q + 3]);
+                    stage_w[row * 4 + (q ^ ((row >> 1) & 3))] = val;
+                  }
+                }
+                __syncwarp();
+                const int row = lane >> 2, pp = it * 8 + row;
+                const uint4 val = stage_w[row * 4 + (j ^ ((row >> 1) & 3))];
+                if (st_ok && ((okmask >> pp) & 1u)) *reinterpret_cast<uint4 *>(obase + spix[it] * p.Cout * 2 + off) = val;
               }
             }
           }
@@ -451,7 +501,7 @@ constexpr int kMaxDevices = 64;
 static std::mutex g_mu;
 static int g_sms[kMaxDevices];
 
-struct Tuning { int debug = 0, bn = 0, stages_a = 0, stages_b = 0, mcast = 1; };
+struct Tuning { int debug = 0, bn = 0, stages_a = 0, stages_b = 0, mcast = 1, stage_small = 1; };
 static const Tuning &tuning() {            // read once at first use; overrides exist only in the test library
   static const Tuning t = [] {
     Tuning v;
@@ -462,6 +512,7 @@ static const Tuning &tuning() {            // read once at first use; overrides 
     v.stages_a = env_int("CTPN_TC_STAGES_A", 0);
     v.stages_b = env_int("CTPN_TC_STAGES_B", 0);
     v.mcast = env_int("CTPN_TC_MCAST", 1);
+    v.stage_small = env_int("CTPN_TC_STAGE_SMALL", 1);
 #endif
     return v;
   }();
@@ -509,7 +560,12 @@ static int cached_tmap(int dev, CUtensorMap *out, const void *ptr, int rank, con
 template <int BN, int P, int TAPS, int MC, int F8 = 0>
 static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, ConvTcParams &p, cudaStream_t st) {
   const size_t a_stage = (size_t)p.planes * p.patch_bytes, b_stage = (size_t)p.planes * BN * 128;
-  const size_t budget = 227 * 1024 - 1024 - kCtrlBytes - kStageBytes;
+  // long-K F16F8 layers: a quarter-size staging block buys a 4th weight stage (their weight stream, not the epilogue, is
+  // what the tensor pipe waits for: 3 stages x 280 ns of MMAs do not cover the L2 latency)
+  const bool small = F8 && TAPS == 9 && p.Cin >= 256 && !(p.flags & (CTPN_F_OUT_F32 | CTPN_F_OUT_BF16X2 | CTPN_F_POOL)) && tuning().stage_small != 0;
+  p.stage_small = small ? 1 : 0;
+  const size_t stage_bytes = small ? kStageBytes / 4 : kStageBytes;
+  const size_t budget = 227 * 1024 - 1024 - kCtrlBytes - stage_bytes;
   // activation ring: two stages when they leave room for at least two weight stages, else one
   int sa = (2 * a_stage + 2 * b_stage <= budget) ? 2 : 1;
   if (p.taps == 1) sa = (int)std::min<size_t>(4, std::max<size_t>(1, (budget / 2) / a_stage));
@@ -520,7 +576,8 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
   if (tuning().stages_b > 0) sb = std::max(1, std::min(sb, tuning().stages_b));
   p.stages_a = sa;
   p.stages_b = sb;
-  const size_t smem = 1024 + sa * a_stage + sb * b_stage + kStageBytes + kCtrlBytes;   // a constant of the instantiation
+  const size_t smem = 1024 + sa * a_stage + sb * b_stage + stage_bytes + kCtrlBytes;
+  CTPN_REQUIRE(smem <= 227 * 1024, "conv_tc: %zu bytes of shared memory", smem);
   auto kernel = conv_tc_kernel<BN, P, TAPS, MC, F8>;
   static bool attr_set[kMaxDevices];
   static int max_clusters[kMaxDevices];     // co-resident 2-CTA clusters of this instantiation (one CTA per SM)
@@ -536,7 +593,7 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
   {
     std::lock_guard<std::mutex> lock(g_mu);
     if (!attr_set[dev]) {
-      CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // the largest layout of any call (stage counts vary per layer)
       if (MC) {
         cfg.gridDim = dim3(2 * (g_sms[dev] / 2));
         int n = 0;
