@@ -24,9 +24,9 @@ constexpr int kHid = 128, kGates = 512;
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// NC = CTAs per cluster (2 or 4): CTA `rank` owns hidden units [rank * 128/NC, (rank + 1) * 128/NC) and the 4 gate columns of
-// each.  NC = 4 halves the resident weight slice (64 KiB), so two CTAs fit on an SM: 16 warps per SM instead of 8 for this
-// latency-bound loop (launched as clusters through cudaLaunchKernelEx).
+// NC = CTAs per cluster: CTA `rank` owns hidden units [rank * 128/NC, (rank + 1) * 128/NC) and the 4 gate columns of each.
+// NC = 2 is the product configuration; NC = 4 (64 KiB weight slice, two CTAs per SM) is a measured dead end kept for the
+// test library only (see ctpn_bilstm_recurrent).
 template <int RG, int NC>
 __global__ void __launch_bounds__(256, NC == 4 ? 2 : 1)
 bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, const float *__restrict__ wh_bw,
@@ -186,14 +186,14 @@ extern "C" int ctpn_bilstm_recurrent(const float *xproj, const float *wh_fw, con
   CTPN_REQUIRE(R > 0 && W > 0, "ctpn_bilstm_recurrent: bad shape R=%d W=%d", R, W);
   CTPN_REQUIRE(planes >= 1 && planes <= 3, "ctpn_bilstm_recurrent: planes must be 1..3");
   cudaStream_t st = (cudaStream_t)stream;
-  // rows per cluster: as many as keeps every SM busy in a single wave.  Large batches: 4-CTA clusters, two CTAs per SM
-  // (R = 1184: 74 clusters x 4 CTAs = 296 = 2 x 148); small ones: 2-CTA clusters of fewer rows each.
+  // rows per cluster: as many as keeps every SM busy in a single wave (148 SMs = 74 2-CTA clusters per direction pair).
+  // The 4-CTA-cluster variant (two CTAs per SM, 16 warps) was measured SLOWER on B200 (0.93 vs 0.67 ms at R = 1184, W = 56:
+  // every row group re-reads the weight slice, so two CTAs per SM double the shared-memory traffic, and the h exchange
+  // and the cluster barrier span four CTAs); it stays selectable in the test library (CTPN_LSTM_NC=4) for that record.
 #ifdef CTPN_DEBUG
   static const int force_nc = [] { const char *e = getenv("CTPN_LSTM_NC"); return e ? atoi(e) : 0; }();
-#else
-  constexpr int force_nc = 0;
+  if (R >= 32 * 37 && force_nc == 4) return launch_bilstm<32, 4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
 #endif
-  if (R >= 32 * 37 && force_nc != 2) return launch_bilstm<32, 4>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
   if (R >= 32 * 37) return launch_bilstm<32, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
   if (R >= 16 * 37) return launch_bilstm<16, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);
   if (R >= 8 * 37) return launch_bilstm<8, 2>(xproj, wh_fw, wh_bw, out_planes, R, W, planes, st);

@@ -323,12 +323,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int chunk = eset; chunk < (CTPN_DBG(p, 16) ? 0 : BN / 32); chunk += 2) {
         uint32_t rr[32];
         tmem_ld_32x32(taddr + chunk * 32, rr);
-        tmem_ld_wait();
         const int c0 = nt * BN + chunk * 32;
         float v[32];
         if (P > 1) {
           uint32_t rc[32];
-          tmem_ld_32x32(taddr + BN + chunk * 32, rc);
+          tmem_ld_32x32(taddr + BN + chunk * 32, rc);     // both accumulators in flight, one wait
           tmem_ld_wait();
           if (F8) {
 #pragma unroll
@@ -338,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + __uint_as_float(rc[i]);
           }
         } else {
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
         }
