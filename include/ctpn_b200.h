@@ -106,6 +106,12 @@ int ctpn_conv1_1_tc(const void *src, int src_is_f32, const float *lut, const flo
 #define CTPN_F_POOL 2
 #define CTPN_F_OUT_F32 4
 #define CTPN_F_OUT_BF16X2 8 /* ctpn_conv3x3_f16f8 only: write two bf16 planes instead of F16F8 planes */
+/* Row-stacked batches: a tensor [B][H + 1][W][C] with one ZERO row after every image is one tall image for the tiling (a 37-row
+ * map wastes 23 % of its 16-row tiles, a 32 x 38-row stack none) while the zero rows keep the images' halos apart.
+ * STACK_IN: the input is stacked (taps = 9, no pooling; H is still the image height).  STACK_OUT: write the output in the
+ * stacked layout [B][Ho + 1][Wo] -- a STACK_IN layer also writes the zero rows, a plain-input layer leaves them to the caller. */
+#define CTPN_F_STACK_IN 16
+#define CTPN_F_STACK_OUT 32
 int ctpn_conv3x3(const void *in_planes, const void *w_planes, const float *bias, void *out, int B,
                  int H, int W, int cin, int cout, int taps, int planes, int flags, void *stream);
 /* The same layers in the "F16F8" arithmetic: 2 tensor-core units per MAC instead of the 3 of two bf16 planes, float32-faithful

@@ -179,6 +179,60 @@ def cmd_conv_f16f8(a):
     return 0 if ok else 1
 
 
+def cmd_conv_stack(a):
+    """Row-stacked batches (CTPN_F_STACK_IN / _OUT): the same layer on [B][H+1][W][C] frames with zero pad rows must give
+    bit-identical image rows to the plain layout, zero pad rows in a stacked output, and compact rows otherwise."""
+    import torch
+    from ctpn_b200 import _native as N
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(a.seed)
+    B, H, W, C, Co = a.B, a.H, a.W, a.cin, a.cout
+    x = torch.relu(torch.randn(B, H, W, C, generator=g))
+    w = torch.randn(9, C, Co, generator=g) * (2.0 / (9 * C)) ** 0.5
+    b = torch.randn(Co, generator=g) * 0.1
+    s_in, t_in = 1.0, _pow2_floor(448.0 / float(x.abs().max())) / 2.0
+    s_w, t_w = _pow2_floor(16384.0 / float(w.abs().max())), _pow2_floor(448.0 / float(w.abs().max()))
+    xh, xc, _ = f16f8_quantize(x, s_in, t_in)
+    plain = torch.cat([xh.view(torch.uint8).reshape(-1), xc.reshape(-1)]).to(dev)
+    xs = torch.zeros(B, H + 1, W, C)
+    xs[:, :H] = x
+    sh, sc, _ = f16f8_quantize(xs, s_in, t_in)
+    stacked = torch.cat([sh.view(torch.uint8).reshape(-1), sc.reshape(-1)]).to(dev)
+    wp = torch.zeros(2 * Co * 9 * C * 2, dtype=torch.uint8, device=dev)
+    N.check(N.lib.ctpn_pack_weights_f16f8(N.ptr(w.to(dev).contiguous()), 9, C, Co, Co, s_w, t_w, N.ptr(wp), N.stream_ptr()), "pack")
+    bd = b.to(dev)
+    inv_main, inv_cross, out_s, out_t = 1.0 / (s_in * s_w), 1.0 / (2048.0 * t_in * t_w), 1.0, 4.0
+
+    def run(inp, flags, nbytes):
+        out = torch.full((nbytes,), 0xAB, dtype=torch.uint8, device=dev)
+        N.check(N.lib.ctpn_conv3x3_f16f8(N.ptr(inp), N.ptr(wp), N.ptr(bd), N.ptr(out), B, H, W, C, Co, 9, flags, inv_main, inv_cross,
+                                         out_s, out_t, N.stream_ptr()), "conv")
+        torch.cuda.synchronize()
+        return out.cpu()
+    n = B * H * W * Co
+    ns = B * (H + 1) * W * Co
+    ref = run(plain, F_RELU, 4 * n)                                     # plain in, plain F16F8 out
+    so = run(stacked, F_RELU | 16 | 32, 4 * ns)                         # stacked in, stacked out
+    co = run(stacked, F_RELU | 16, 4 * n)                               # stacked in, compact out
+    cb = run(stacked, F_RELU | 16 | 8, 4 * n)                           # stacked in, compact bf16x2 out
+    rb = run(plain, F_RELU | 8, 4 * n)
+    ok_compact = bool(torch.equal(co, ref)) and bool(torch.equal(cb, rb))
+    h_ref, c_ref = ref[:2 * n].view(B, H, W * Co * 2), ref[2 * n:].view(B, H, W * Co * 2)
+    h_so, c_so = so[:2 * ns].view(B, H + 1, W * Co * 2), so[2 * ns:].view(B, H + 1, W * Co * 2)
+    ok_rows = bool(torch.equal(h_so[:, :H], h_ref)) and bool(torch.equal(c_so[:, :H], c_ref))
+    ok_pad = bool((h_so[:, H] == 0).all()) and bool((c_so[:, H] == 0).all())
+    # pooled layer writing a stacked output: image rows equal the plain pooled output, pad rows untouched (0xAB here)
+    pp = run(plain, F_RELU | F_POOL, 4 * B * (H // 2) * (W // 2) * Co)
+    ps = run(plain, F_RELU | F_POOL | 32, 4 * B * (H // 2 + 1) * (W // 2) * Co)
+    n2, n2s = B * (H // 2) * (W // 2) * Co, B * (H // 2 + 1) * (W // 2) * Co
+    ok_pool = bool(torch.equal(ps[:2 * n2s].view(B, H // 2 + 1, -1)[:, :H // 2], pp[:2 * n2].view(B, H // 2, -1))) and \
+        bool(torch.equal(ps[2 * n2s:].view(B, H // 2 + 1, -1)[:, :H // 2], pp[2 * n2:].view(B, H // 2, -1))) and \
+        bool((ps[:2 * n2s].view(B, H // 2 + 1, -1)[:, H // 2] == 0xAB).all())
+    ok = ok_compact and ok_rows and ok_pad and ok_pool
+    print(json.dumps(dict(ok=ok, compact=ok_compact, rows=ok_rows, pad_zero=ok_pad, pooled_stack_out=ok_pool)))
+    return 0 if ok else 1
+
+
 def cmd_conv1(a):
     """conv1_1 (tensor-core im2col-in-smem kernel or the SIMT one) against float64 on the same uint8 image."""
     import torch
@@ -294,13 +348,16 @@ def main():
     for k, d in dict(B=1, H=8, W=16, cin=64, cout=64, taps=9, flags=0, seed=0).items():
         cq.add_argument("--" + k, type=int, default=d)
     cq.add_argument("--xscale", type=float, default=1.0)
+    cs = sub.add_parser("conv_stack")
+    for k, d in dict(B=3, H=37, W=56, cin=128, cout=128, seed=0).items():
+        cs.add_argument("--" + k, type=int, default=d)
     ns = sub.add_parser("net_simt")
     for k, d in dict(B=3, H=128, W=192, planes=2).items():
         ns.add_argument("--" + k, type=int, default=d)
     ns.add_argument("--tol", type=float, default=5e-4)
     sub.add_parser("proposals_generic")
     a = ap.parse_args()
-    return {"conv": cmd_conv, "conv_f16f8": cmd_conv_f16f8, "conv1": cmd_conv1, "bilstm": cmd_bilstm, "net_simt": cmd_net_simt,
+    return {"conv": cmd_conv, "conv_f16f8": cmd_conv_f16f8, "conv_stack": cmd_conv_stack, "conv1": cmd_conv1, "bilstm": cmd_bilstm, "net_simt": cmd_net_simt,
             "proposals_generic": cmd_proposals_generic}[a.cmd](a)
 
 

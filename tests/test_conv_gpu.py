@@ -80,6 +80,12 @@ def test_conv_f16f8(case):
     run_check("conv_f16f8", "--B", B, "--H", H, "--W", W, "--cin", cin, "--cout", cout, "--taps", taps, "--flags", flags, "--xscale", xs)
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", [(3, 37, 56, 128, 128), (5, 9, 20, 64, 64), (2, 75, 40, 256, 128)])
+def test_conv_row_stacked_batches(B, H, W, cin, cout):
+    """CTPN_F_STACK_IN / _OUT: one tall image with zero pad rows between the images == the per-image layout, bit for bit."""
+    run_check("conv_stack", "--B", B, "--H", H, "--W", W, "--cin", cin, "--cout", cout)
+
+
 SIMT_CASES = [
     (1, 13, 17, 64, 64, 9, 2, RELU),
     (2, 20, 30, 64, 128, 9, 3, RELU | POOL),

@@ -63,6 +63,12 @@ struct ConvTcParams {
   // F16F8 arithmetic (common.cuh): value = main * inv_main + cross * inv_cross; outputs are re-quantised as
   // h = fp16(v * out_s), e4m3(v * out_t), e4m3((v * out_s - h) * out_rs) with out_rs = 2^11 * out_t / out_s
   float inv_main, inv_cross, out_s, out_t, out_rs;
+  // Row-stacked batches (CTPN_F_STACK_IN / _OUT): images stored as [B][H + 1][W][C] with one zero row after every image, so the
+  // batch is ONE tall image for the tiling (a 37-row map wastes 23 % of its 16-row tiles, the 32 x 38-row stack 0 %) while the
+  // zero rows keep the images' halos apart.  in_stack_h = rows per image incl. the pad row in the kernel's input frame (0 =
+  // plain); out_rows = rows per image of the OUTPUT frame (Ho, or Ho + 1 when the output is stacked too).
+  int in_stack_h, out_rows, out_stacked;
+  double work;              // algorithmic FLOPs of the call (profiling label only)
   int stage_small;          // 1: 512-byte staging block per epilogue warp (8 pixels per round) -- frees room for a 4th weight stage
 };
 
@@ -294,16 +300,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       unit_tile(u, mt, nt);
       const int b = mt / tiles_per_img, r = mt % tiles_per_img;
       const int y = (r / p.tiles_x) * p.TH + th, x = (r % p.tiles_x) * p.TW + tw;
-      bool ok;
-      int oy, ox;
+      bool ok, live = true;       // live = false: a pad row of a stacked frame (stored as zeros when the output is stacked)
+      int oy, ox, ob = b;
       if (pool) {
         oy = y >> 1; ox = x >> 1;
         ok = !(th & 1) && !(tw & 1) && oy < p.Ho && ox < p.Wo;
       } else {
         oy = y; ox = x;
         ok = y < p.H && x < p.W;
+        if (p.in_stack_h) {       // stacked input: y runs over the whole stack (the kernel sees one image of B * in_stack_h rows)
+          ob = y / p.in_stack_h;
+          oy = y - ob * p.in_stack_h;
+          live = oy < p.in_stack_h - 1;
+          if (!p.out_stacked) ok = ok && live;
+        }
       }
-      const long long pix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+      const long long pix = ((long long)ob * p.out_rows + oy) * p.Wo + ox;
       // coalesced plane stores: the warp's 32-pixel x 32-channel block is transposed through shared memory so
       // that 4 consecutive lanes write the 64 contiguous bytes of one pixel (full 32-B sectors) instead of every
       // lane writing 16 B of its own pixel.  Lane l stores for pixels (l >> 2) + 8 * it, 16-byte chunk l & 3.
@@ -353,6 +365,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
         if (pool) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -368,7 +384,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           float x[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) x[k] = j == 0 ? v[k] : j == 1 ? v[8 + k] : j == 2 ? v[16 + k] : v[24 + k];
-          const bool okw = oy < p.Ho && ox < p.Wo;
+          const bool okw = oy < p.Ho && ox < p.Wo;     // (pix already points into the stacked frame when out_rows = Ho + 1)
           float r[8];
           uint4 hw;
           hw.x = f16x2_split(x[0] * p.out_s, x[1] * p.out_s, r[0], r[1]);
@@ -606,7 +622,7 @@ static int launch_bn(int dev, const CUtensorMap &ta, const CUtensorMap &tb, Conv
   }
   char label[128];
   if (prof_enabled()) snprintf(label, sizeof(label), "conv_tc t%d %dx%dx%d c%d-%d %s%d bn%d%s", p.taps, p.B, p.H, p.W, p.Cin, p.Cout, F8 ? "f16f8 p" : "p", p.planes, BN, MC ? " mc" : "");
-  ProfScope prof(label, 2.0 * p.B * p.H * p.W * (double)p.taps * p.Cin * p.Cout, st);
+  ProfScope prof(label, p.work, st);
   if (MC) cfg.gridDim = dim3(2 * std::min(max_clusters[dev], p.total_units));
   else cfg.gridDim = dim3(std::min(p.total_units, g_sms[dev]));
   CTPN_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, p));
@@ -632,6 +648,15 @@ static int conv_tc_run(const void *in_planes, const void *w_planes, const float 
   CTPN_REQUIRE(B > 0 && H > 0 && W > 0, "ctpn_conv3x3: bad shape");
   const bool pool = flags & CTPN_F_POOL;
   CTPN_REQUIRE(!pool || (taps == 9 && H >= 2 && W >= 2), "ctpn_conv3x3: pooling needs taps=9 and H,W >= 2");
+  const bool stack_in = flags & CTPN_F_STACK_IN, stack_out = flags & CTPN_F_STACK_OUT;
+  CTPN_REQUIRE(!stack_in || (taps == 9 && !pool), "ctpn_conv3x3: CTPN_F_STACK_IN needs taps=9 and no pooling");
+  CTPN_REQUIRE(!stack_out || !(flags & CTPN_F_OUT_F32), "ctpn_conv3x3: stacked output is a plane format");
+  const int img_B = B, img_H = H;
+  if (stack_in) {          // the kernel sees one image of B * (H + 1) rows
+    CTPN_REQUIRE((long long)B * (H + 1) < (1ll << 30), "ctpn_conv3x3: stack too tall");
+    H = B * (H + 1);
+    B = 1;
+  }
   int dev = 0, rc;
   CTPN_CUDA(cudaGetDevice(&dev));
   CTPN_REQUIRE(dev >= 0 && dev < kMaxDevices, "ctpn_conv3x3: device index %d not supported", dev);
@@ -662,7 +687,12 @@ static int conv_tc_run(const void *in_planes, const void *w_planes, const float 
   p.Wo = pool ? W / 2 : W;
   p.bias = bias;
   p.out = out;
-  p.out_plane_stride = (long long)B * p.Ho * p.Wo * cout;
+  p.work = 2.0 * img_B * img_H * W * (double)taps * cin * cout;
+  p.in_stack_h = stack_in ? img_H + 1 : 0;
+  const int img_Ho = pool ? img_H / 2 : img_H;
+  p.out_rows = img_Ho + (stack_out ? 1 : 0);
+  p.out_stacked = stack_out ? 1 : 0;
+  p.out_plane_stride = (long long)img_B * p.out_rows * p.Wo * cout;
   p.cout_pad = cout;
   if (f8) {
     CTPN_REQUIRE(q->inv_main > 0.f && q->inv_cross > 0.f && q->out_s > 0.f && q->out_t > 0.f, "ctpn_conv3x3_f16f8: scales must be positive");

@@ -30,7 +30,7 @@ static const char *kFw = "lstm_o/bidirectional_rnn/fw/lstm_cell";
 static const char *kBw = "lstm_o/bidirectional_rnn/bw/lstm_cell";
 static const double kPixelMeans[3] = {102.9801, 115.9465, 122.7717};   // lib/fast_rcnn/config.py:200 (BGR)
 
-struct Tap { const void *ptr; long long pixels; int channels; bool planes; float q_s = 0.f, q_t = 0.f; };   // q_s > 0: F16F8 planes
+struct Tap { const void *ptr; long long pixels; int channels; bool planes; float q_s = 0.f, q_t = 0.f; int stack_h = 0, stack_w = 0; };   // q_s > 0: F16F8 planes; stack_h > 0: rows stacked as [B][h + 1][w]
 
 }  // namespace ctpn
 
@@ -187,6 +187,7 @@ static int finalize(ctpn_net *n) {
 }
 
 struct NetLayout {
+  bool stack;           // F16F8: conv4_3's pooled output and conv5_1..conv5_3 outputs are row-stacked ([B][h + 1][w], zero pad rows)
   size_t act[16];       // offsets of the 14 conv outputs + lstm_out + fc_out
   size_t xproj, heads, total;
   int h[15], w[15];     // spatial size of each conv output
@@ -204,6 +205,10 @@ static NetLayout net_layout(const ctpn_net *n, int B, int H, int W) {
     sizes[l] = (size_t)P * B * h * w * kConvs[l].cout * 2;
   }
   L.fh = h; L.fw = w;
+  // stack the 1/16-scale maps when one tall image needs fewer 16-row tiles than B separate ones (37 rows: 76 vs 96 at B = 32)
+  L.stack = n->f16f8 && ((long long)B * (h + 1) + 15) / 16 < (long long)B * ((h + 15) / 16);
+  if (L.stack)
+    for (int l = 9; l <= 12; ++l) sizes[l] = (size_t)P * B * (h + 1) * w * kConvs[l].cout * 2;
   const size_t M = (size_t)B * h * w;
   sizes[14] = (size_t)P * M * 256 * 2;   // lstm_out
   sizes[15] = (size_t)P * M * 512 * 2;   // lstm_o (FC)
@@ -235,15 +240,19 @@ __global__ void split_heads_kernel(const float *__restrict__ heads, long long M,
 
 // F16F8 planes -> float32: (h + residual / (2^11 t / s)) / s
 __global__ void f16f8_to_f32_kernel(const __half *__restrict__ hi, const uint8_t *__restrict__ cross, long long n, int C, float s, float t,
-                                    float *__restrict__ dst) {
+                                    int stack_h, int stack_w, float *__restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const long long pix = i / C;
+  long long pix = i / C;
   const int c = (int)(i % C);
+  if (stack_h) {     // compact pixel index -> position in the stacked frame [B][stack_h + 1][stack_w]
+    const long long per = (long long)stack_h * stack_w, b = pix / per, r = pix % per;
+    pix = b * (stack_h + 1) * stack_w + r;
+  }
   const uint8_t rb = cross[pix * 2 * C + (c >> 6) * 128 + 64 + (c & 63)];
   const __half_raw hr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)rb, __NV_E4M3);
   const float r = __half2float(__half(hr)) / (kResidualGain * t / s);
-  dst[i] = (__half2float(hi[i]) + r) / s;
+  dst[i] = (__half2float(hi[pix * C + c]) + r) / s;
 }
 
 __global__ void planes_to_f32_kernel(const __nv_bfloat16 *__restrict__ src, long long n, long long plane_stride, int planes,
@@ -268,10 +277,12 @@ __global__ void absmax_f16_kernel(const __half *__restrict__ x, long long n, uns
 }
 
 // one 3x3 layer (or conv1_1 for l = 0) in the F16F8 arithmetic with the scales currently in the net
-static int run_layer_f16f8(ctpn_net *n, int l, const void *in, void *out, int B, int h, int w, void *stream) {
+static int run_layer_f16f8(ctpn_net *n, int l, const void *in, void *out, int B, int h, int w, bool stack, void *stream) {
   const ConvSpec &s = kConvs[l];
   if (l == 0) return ctpn_conv1_1_tc_f16f8(in, 0, n->lut, n->c11_w, n->c11_b, out, B, h, w, n->act_s[0], n->act_t[0], stream);
-  const int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0) | (l == 13 ? CTPN_F_OUT_BF16X2 : 0);   // rpn_conv feeds the bf16x2 matmuls
+  int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0) | (l == 13 ? CTPN_F_OUT_BF16X2 : 0);   // rpn_conv feeds the bf16x2 matmuls
+  if (stack && l >= 9 && l <= 12) flags |= CTPN_F_STACK_OUT;
+  if (stack && l >= 10) flags |= CTPN_F_STACK_IN;
   const float inv_main = 1.f / (n->act_s[l - 1] * n->w_s[l]), inv_cross = 1.f / (kResidualGain * n->act_t[l - 1] * n->w_t[l]);
   return ctpn_conv3x3_f16f8(in, n->conv_w[l], n->conv_b[l], out, B, h, w, s.cin, s.cout, 9, flags, inv_main, inv_cross,
                             l == 13 ? 1.f : n->act_s[l], l == 13 ? 1.f : n->act_t[l], stream);
@@ -285,13 +296,15 @@ static int calibrate_f16f8(ctpn_net *n, const void *images, int src_is_f32, int 
   int h = H, w = W;
   for (int l = 0; l < 13; ++l) {
     const void *in = l == 0 ? images : (const void *)(ws + L.act[l - 1]);
+    if (L.stack && l == 9)      // pad rows of conv4_3's stacked output (see ctpn_net_forward)
+      CTPN_CUDA(cudaMemsetAsync(ws + L.act[9], 0, (size_t)n->planes * B * (L.h[9] + 1) * L.w[9] * kConvs[9].cout * 2, st));
     float s_try = 1.f;
     for (int attempt = 0; ; ++attempt) {
       n->act_s[l] = s_try; n->act_t[l] = 1.f;
       int rc = l == 0 ? ctpn_conv1_1_tc_f16f8(images, src_is_f32, n->lut, n->c11_w, n->c11_b, ws + L.act[0], B, h, w, s_try, 1.f, stream)
-                      : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, stream);
+                      : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, L.stack, stream);
       if (rc) return rc;
-      const long long cnt = (long long)B * L.h[l] * L.w[l] * kConvs[l].cout;
+      const long long cnt = (long long)B * (L.h[l] + ((L.stack && l >= 9 && l <= 12) ? 1 : 0)) * L.w[l] * kConvs[l].cout;
       CTPN_CUDA(cudaMemsetAsync(n->absmax_dev, 0, sizeof(unsigned), st));
       absmax_f16_kernel<<<1184, 256, 0, st>>>((const __half *)(ws + L.act[l]), cnt, n->absmax_dev);
       CTPN_LAUNCH_CHECK();
@@ -313,7 +326,7 @@ static int calibrate_f16f8(ctpn_net *n, const void *images, int src_is_f32, int 
       break;
     }
     int rc = l == 0 ? ctpn_conv1_1_tc_f16f8(images, src_is_f32, n->lut, n->c11_w, n->c11_b, ws + L.act[0], B, h, w, n->act_s[0], n->act_t[0], stream)
-                    : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, stream);
+                    : run_layer_f16f8(n, l, in, ws + L.act[l], B, h, w, L.stack, stream);
     if (rc) return rc;
     h = L.h[l]; w = L.w[l];
   }
@@ -393,11 +406,15 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
     if ((rc = ctpn_conv1_1_tc_f16f8(images, src_is_f32, net->lut, net->c11_w, net->c11_b, ws + L.act[0], B, H, W, net->act_s[0], net->act_t[0], stream))) return rc;
     net->taps["conv1_1"] = Tap{ws + L.act[0], (long long)B * H * W, 64, true, net->act_s[0], net->act_t[0]};
     for (int l = 1; l < 14; ++l) {
-      if ((rc = run_layer_f16f8(net, l, ws + L.act[l - 1], ws + L.act[l], B, hh, ww, stream))) return rc;
+      if (L.stack && l == 9)      // conv4_3 writes only the image rows of its stacked output: the pad rows must be zero
+        CTPN_CUDA(cudaMemsetAsync(ws + L.act[9], 0, (size_t)P * B * (L.h[9] + 1) * L.w[9] * kConvs[9].cout * 2, (cudaStream_t)stream));
+      if ((rc = run_layer_f16f8(net, l, ws + L.act[l - 1], ws + L.act[l], B, hh, ww, L.stack, stream))) return rc;
       hh = L.h[l]; ww = L.w[l];
       const ConvSpec &s = kConvs[l];
+      const bool stacked = L.stack && l >= 9 && l <= 12;
       net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] =
-          Tap{ws + L.act[l], (long long)B * hh * ww, s.cout, true, l == 13 ? 0.f : net->act_s[l], l == 13 ? 0.f : net->act_t[l]};
+          Tap{ws + L.act[l], (long long)B * hh * ww, s.cout, true, l == 13 ? 0.f : net->act_s[l], l == 13 ? 0.f : net->act_t[l],
+              stacked ? hh : 0, stacked ? ww : 0};
     }
   }
 #ifdef CTPN_DEBUG
@@ -445,8 +462,9 @@ extern "C" int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_
   if (!out_f32) return CTPN_OK;
   CTPN_REQUIRE(capacity >= (size_t)n, "ctpn_net_debug_tap: buffer too small (%zu < %lld)", capacity, n);
   if (t.planes && t.q_s > 0.f) {
-    f16f8_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half *)t.ptr, (const uint8_t *)t.ptr + n * 2, n,
-                                                                                       t.channels, t.q_s, t.q_t, out_f32);
+    const long long stored = t.stack_h ? n / t.stack_h * (t.stack_h + 1) : n;      // elements per plane incl. pad rows
+    f16f8_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __half *)t.ptr, (const uint8_t *)t.ptr + stored * 2, n,
+                                                                                       t.channels, t.q_s, t.q_t, t.stack_h, t.stack_w, out_f32);
     CTPN_LAUNCH_CHECK();
   } else if (t.planes) {
     planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)t.ptr, n, n, net->planes, out_f32);
