@@ -151,6 +151,23 @@ def test_reference_api_test_ctpn_and_text_detector(weights):
         assert lines.ndim == 2 and lines.shape[1] == 9 and lines.dtype == np.float64
 
 
+@pytest.mark.parametrize("h,w,n", [(128, 192, 3), (600, 900, 2), (300, 300, 5)])
+def test_f16f8_batch_equals_singles_row_stacked_maps(weights, h, w, n):
+    """F16F8 mode stores the 1/16-scale maps of a batch row-stacked (one tall image with zero pad rows, fewer 16-row tiles);
+    a single image is not stacked.  Same calibrated scales -> the batched results must equal the per-image ones bit for bit."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, mode="f16f8")
+    ims = np.stack([synth.make_image(80 + i, h, w) for i in range(n)])
+    batch = eng.detect_batch(ims)                 # first call: calibrates the activation scales on this batch
+    cls_b, box_b = eng.forward_heads(torch.from_numpy(ims).cuda())
+    for i in range(n):
+        s, b = eng.detect(ims[i])
+        np.testing.assert_array_equal(s, batch[i][0])
+        np.testing.assert_array_equal(b, batch[i][1])
+        c1, b1 = eng.forward_heads(torch.from_numpy(ims[i:i + 1]).cuda())
+        assert torch.equal(c1[0], cls_b[i]) and torch.equal(b1[0], box_b[i])
+
+
 def test_demo_pb_frozen_graph_path_equals_checkpoint_path(weights, tmp_path, monkeypatch):
     """ctpn/demo_pb.py (demo_pb.py:55-98 of the reference): weights from a frozen GraphDef, head tensors fetched by graph name,
     proposal_layer called directly, TextDetector, res file -- the same result file as ctpn/demo.py's ctpn() on that image."""
