@@ -464,9 +464,10 @@ def main():
         other = [p for p in prof if not p["kernel"].startswith("conv_tc")]
         c11_ms = sum(p["ms"] for p in c11) / K
         lstm_ms = sum(p["ms"] for p in lstm) / K
-        c11_bytes = sum(H * W * (3 + 64 * M["planes"] * 2) for H, W in shapes) * per_shape
+        store_planes = 2 if mode == "f16f8" else M["planes"]          # F16F8 stores fp16 + 2 x e4m3 = the bytes of two bf16 planes
+        c11_bytes = sum(H * W * (3 + 64 * store_planes * 2) for H, W in shapes) * per_shape
         lstm_flops = sum(w["recurrent"] for w in works) * per_shape
-        lstm_bytes = sum(w["cells"] * (1024 * 4 + 256 * 2 * M["planes"]) for w in works) * per_shape
+        lstm_bytes = sum(w["cells"] * (1024 * 4 + 256 * 2 * min(store_planes, 3)) for w in works) * per_shape
         fma_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12     # fp32 FMA lanes x 2 flop x max clock
         line = {
             "metric": metric_name(cfg), "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W_,
@@ -491,7 +492,7 @@ def main():
             "roofline_extra": [
                 {"kernel": "conv1_tc_kernel (conv1_1)", "bound": "hbm", "achieved": c11_bytes / max(c11_ms, 1e-9) / 1e6, "peak": hbm, "unit": "GB/s",
                  "frac": c11_bytes / max(c11_ms, 1e-9) / 1e6 / hbm, "ms_per_step": c11_ms,
-                 "note": "algorithmic bytes = 3 B in + 64 ch x %d planes x 2 B out per pixel" % M["planes"]},
+                 "note": "algorithmic bytes = 3 B in + 64 ch x %d planes x 2 B out per pixel" % store_planes},
                 {"kernel": "bilstm_kernel (recurrence)", "bound": "fp32 FMA (latency-bound in practice)", "achieved": lstm_flops / max(lstm_ms, 1e-9) / 1e9,
                  "peak": fma_peak, "unit": "TFLOP/s", "frac": lstm_flops / max(lstm_ms, 1e-9) / 1e9 / fma_peak, "ms_per_step": lstm_ms,
                  "hbm_frac": lstm_bytes / max(lstm_ms, 1e-9) / 1e6 / hbm,

@@ -110,6 +110,26 @@ __device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
   return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
+// four values -> their F16F8 words: two fp16x2 words (of v * s), e4m3x4 of v * t, e4m3x4 of the residuals * rs.
+// The scalings run as packed mul.rn.f32x2 (sm_100); s == 1 (no fp16 pre-scale, the usual case) skips its multiply.
+__device__ __forceinline__ void f16f8_quad(float v0, float v1, float v2, float v3, float s, float t, float rs, uint32_t &h01,
+                                           uint32_t &h23, uint32_t &qv, uint32_t &qr) {
+  const float2 a = make_float2(v0, v1), b = make_float2(v2, v3);
+  float2 as = a, bs = b;
+  if (s != 1.f) {
+    as = __fmul2_rn(a, make_float2(s, s));
+    bs = __fmul2_rn(b, make_float2(s, s));
+  }
+  float2 ra, rb;
+  h01 = f16x2_split(as.x, as.y, ra.x, ra.y);
+  h23 = f16x2_split(bs.x, bs.y, rb.x, rb.y);
+  const float2 at = __fmul2_rn(a, make_float2(t, t)), bt = __fmul2_rn(b, make_float2(t, t));
+  qv = e4m3x4(at.x, at.y, bt.x, bt.y);
+  ra = __fmul2_rn(ra, make_float2(rs, rs));
+  rb = __fmul2_rn(rb, make_float2(rs, rs));
+  qr = e4m3x4(ra.x, ra.y, rb.x, rb.y);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
   return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }

@@ -283,11 +283,7 @@ conv1_tc_kernel(const Conv1TcParams p) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float v0 = fmaxf(v[4 * i], 0.f), v1 = fmaxf(v[4 * i + 1], 0.f), v2 = fmaxf(v[4 * i + 2], 0.f), v3 = fmaxf(v[4 * i + 3], 0.f);
-            float r0, r1, r2, r3;
-            wh[2 * i] = f16x2_split(v0 * p.out_s, v1 * p.out_s, r0, r1);
-            wh[2 * i + 1] = f16x2_split(v2 * p.out_s, v3 * p.out_s, r2, r3);
-            wq[i] = e4m3x4(v0 * p.out_t, v1 * p.out_t, v2 * p.out_t, v3 * p.out_t);
-            wq[8 + i] = e4m3x4(r0 * p.out_rs, r1 * p.out_rs, r2 * p.out_rs, r3 * p.out_rs);
+            f16f8_quad(v0, v1, v2, v3, p.out_s, p.out_t, p.out_rs, wh[2 * i], wh[2 * i + 1], wq[i], wq[8 + i]);
           }
 #pragma unroll
           for (int pl = 0; pl < 2; ++pl) {

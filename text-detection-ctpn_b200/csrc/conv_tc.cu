@@ -385,16 +385,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 8; ++k) x[k] = j == 0 ? v[k] : j == 1 ? v[8 + k] : j == 2 ? v[16 + k] : v[24 + k];
           const bool okw = oy < p.Ho && ox < p.Wo;     // (pix already points into the stacked frame when out_rows = Ho + 1)
-          float r[8];
           uint4 hw;
-          hw.x = f16x2_split(x[0] * p.out_s, x[1] * p.out_s, r[0], r[1]);
-          hw.y = f16x2_split(x[2] * p.out_s, x[3] * p.out_s, r[2], r[3]);
-          hw.z = f16x2_split(x[4] * p.out_s, x[5] * p.out_s, r[4], r[5]);
-          hw.w = f16x2_split(x[6] * p.out_s, x[7] * p.out_s, r[6], r[7]);
-          const uint2 qv = make_uint2(e4m3x4(x[0] * p.out_t, x[1] * p.out_t, x[2] * p.out_t, x[3] * p.out_t),
-                                      e4m3x4(x[4] * p.out_t, x[5] * p.out_t, x[6] * p.out_t, x[7] * p.out_t));
-          const uint2 qr = make_uint2(e4m3x4(r[0] * p.out_rs, r[1] * p.out_rs, r[2] * p.out_rs, r[3] * p.out_rs),
-                                      e4m3x4(r[4] * p.out_rs, r[5] * p.out_rs, r[6] * p.out_rs, r[7] * p.out_rs));
+          uint2 qv, qr;
+          f16f8_quad(x[0], x[1], x[2], x[3], p.out_s, p.out_t, p.out_rs, hw.x, hw.y, qv.x, qr.x);
+          f16f8_quad(x[4], x[5], x[6], x[7], p.out_s, p.out_t, p.out_rs, hw.z, hw.w, qv.y, qr.y);
           if (okw && c0 < p.Cout && !CTPN_DBG(p, 8)) {
             uint8_t *o0 = reinterpret_cast<uint8_t *>(p.out) + pix * p.Cout * 2;
             uint8_t *o1 = o0 + p.out_plane_stride * 2 + (long long)(c0 >> 6) * 128 + (c0 & 63) + j * 8;
@@ -407,11 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t wh[16], wq[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float r0, r1, r2, r3;
-            wh[2 * i] = f16x2_split(v[4 * i] * p.out_s, v[4 * i + 1] * p.out_s, r0, r1);
-            wh[2 * i + 1] = f16x2_split(v[4 * i + 2] * p.out_s, v[4 * i + 3] * p.out_s, r2, r3);
-            wq[i] = e4m3x4(v[4 * i] * p.out_t, v[4 * i + 1] * p.out_t, v[4 * i + 2] * p.out_t, v[4 * i + 3] * p.out_t);
-            wq[8 + i] = e4m3x4(r0 * p.out_rs, r1 * p.out_rs, r2 * p.out_rs, r3 * p.out_rs);
+            f16f8_quad(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], p.out_s, p.out_t, p.out_rs, wh[2 * i], wh[2 * i + 1], wq[i], wq[8 + i]);
           }
           const int j = lane & 3;
 #pragma unroll

@@ -46,7 +46,7 @@ nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ counts
       u64 bits = 0;
       int start = (rb == cb) ? t + 1 : 0;
       for (int i = start; i < col_size; ++i) {
-        if (iou_exact(me, sme, cbox[i], carea[i]) > thresh) bits |= 1ULL << i;
+        if (iou_above(me, sme, cbox[i], carea[i], thresh)) bits |= 1ULL << i;
       }
       mask[((size_t)img * max_n + row) * col_blocks + cb] = bits;
     }

@@ -286,7 +286,7 @@ proposal_column_nms_kernel(const float4 *__restrict__ sorted_boxes, const int *_
     u64 bits = 0;
     const int j0 = wj * 64;
     for (int jj = max(0, i + 1 - j0); jj < 64 && j0 + jj < nc; ++jj)
-      if (iou_exact(me, sme, box[j0 + jj], area[j0 + jj]) > thresh) bits |= 1ULL << jj;
+      if (iou_above(me, sme, box[j0 + jj], area[j0 + jj], thresh)) bits |= 1ULL << jj;
     mask[(size_t)i * wc + wj] = bits;
   }
   __syncthreads();
