@@ -23,11 +23,20 @@ namespace ctpn {
 constexpr int kHid = 128, kGates = 512;
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Cell non-linearities on the special-function unit (ex2.approx + rcp.approx, ~3e-7 absolute error) for the modes whose
+// tolerance is >= 1e-5; the float32-equivalent mode (planes = 3) keeps expf / tanhf / IEEE division.  The accurate versions
+// cost about as many instructions per step as the whole mat-vec.
+template <bool FAST> __device__ __forceinline__ float lstm_sigmoid(float x) {
+  return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : sigmoidf_acc(x);
+}
+template <bool FAST> __device__ __forceinline__ float lstm_tanh(float x) {
+  return FAST ? __fmaf_rn(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * x)), -1.0f) : tanhf(x);
+}
 
 // NC = CTAs per cluster: CTA `rank` owns hidden units [rank * 128/NC, (rank + 1) * 128/NC) and the 4 gate columns of each.
 // NC = 2 is the product configuration; NC = 4 (64 KiB weight slice, two CTAs per SM) is a measured dead end kept for the
 // test library only (see ctpn_bilstm_recurrent).
-template <int RG, int NC>
+template <int RG, int NC, bool FAST>
 __global__ void __launch_bounds__(256, NC == 4 ? 2 : 1)
 bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, const float *__restrict__ wh_bw,
               __nv_bfloat16 *__restrict__ out, int R, int W, int planes) {
@@ -134,8 +143,8 @@ bilstm_kernel(const float *__restrict__ xproj, const float *__restrict__ wh_fw, 
       const int r = (t / kUnits) + (256 / kUnits) * q;
       const float gi = gates[r * kLocalCols + ul], gj = gates[r * kLocalCols + kUnits + ul];
       const float gf = gates[r * kLocalCols + 2 * kUnits + ul], go = gates[r * kLocalCols + 3 * kUnits + ul];
-      const float c = sigmoidf_acc(gf + 1.0f) * c_state[q] + sigmoidf_acc(gi) * tanhf(gj);
-      const float h = sigmoidf_acc(go) * tanhf(c);
+      const float c = lstm_sigmoid<FAST>(gf + 1.0f) * c_state[q] + lstm_sigmoid<FAST>(gi) * lstm_tanh<FAST>(gj);
+      const float h = lstm_sigmoid<FAST>(go) * lstm_tanh<FAST>(c);
       c_state[q] = c;
       const int u = rank * kUnits + ul;
 #pragma unroll
@@ -157,7 +166,7 @@ static int launch_bilstm(const float *xproj, const float *wh_fw, const float *wh
                          cudaStream_t st) {
   constexpr int kLocalCols = 4 * kHid / NC;
   const size_t smem = (size_t)(kHid * kLocalCols + 2 * RG * kHid + RG * kLocalCols) * sizeof(float);
-  auto kernel = bilstm_kernel<RG, NC>;
+  auto kernel = planes <= 2 ? bilstm_kernel<RG, NC, true> : bilstm_kernel<RG, NC, false>;
   CTPN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups = (R + RG - 1) / RG;
   ProfScope prof("bilstm_recurrent", 2.0 * 2.0 * R * W * 128.0 * 512.0, st);
