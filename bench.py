@@ -326,12 +326,30 @@ def main():
         infos.append(torch.tensor([[H, W, 1.0]] * per_shape, dtype=torch.float32, device=dev))
     post = eng.result_rows()
 
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    inflight = []            # (packed, gathered) of the steps whose all-gather may still be running
+
     def step_device():
         outs = [eng.detect_packed(im, info) for im, info in zip(images, infos)]
         if world > 1:
+            # the one collective of the path: all-gather of this step's packed results, issued on a side stream behind an
+            # event of the compute stream so that it overlaps the next step (drained before the timed region closes)
             from ctpn_b200.dist import gather_packed
-            outs = [gather_packed(torch.cat(outs) if len(outs) > 1 else outs[0])]
+            packed = torch.cat(outs) if len(outs) > 1 else outs[0]
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            with torch.cuda.stream(gather_stream):
+                gather_stream.wait_event(done)
+                gathered = gather_packed(packed)
+            inflight.append((packed, gathered))
+            if len(inflight) > 4:
+                inflight.pop(0)
+            outs = [gathered]
         return outs
+
+    def drain():
+        if gather_stream is not None:
+            torch.cuda.current_stream().wait_stream(gather_stream)
 
     def barrier():
         if world > 1:
@@ -372,6 +390,7 @@ def main():
     e0.record()
     for _ in range(K):
         step_device()
+    drain()
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))

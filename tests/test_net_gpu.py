@@ -168,6 +168,29 @@ def test_f16f8_batch_equals_singles_row_stacked_maps(weights, h, w, n):
         assert torch.equal(c1[0], cls_b[i]) and torch.equal(b1[0], box_b[i])
 
 
+def test_small_batches_replay_a_cuda_graph_per_shape_bucket(weights):
+    """Batches of <= graph_max_batch images run as a CUDA graph captured on the third call of a (shape, dtype) bucket; the
+    replayed results must equal the eager ones bit for bit, also when two buckets alternate and inputs change between calls."""
+    from ctpn_b200 import Engine
+    eager = Engine(weights, planes=2, graph_max_batch=0)
+    eng = Engine(weights, planes=2)
+    a = [synth.make_image(90 + i, 96, 160) for i in range(4)]
+    b = [synth.make_image(95 + i, 160, 96) for i in range(4)]
+    for rnd in range(4):                                    # calls 1-2 eager, 3 captures + replays, 4 replays
+        for im in (a[rnd], b[rnd]):
+            s0, b0 = eager.detect(im)
+            s1, b1 = eng.detect(im)
+            np.testing.assert_array_equal(s1, s0)
+            np.testing.assert_array_equal(b1, b0)
+    assert sum("graph" in g for g in eng._graphs.values()) == 2
+    pair = np.stack(a[:2])                                  # batch 2 is its own bucket
+    for _ in range(4):
+        got = eng.detect_batch(pair)
+        want = eager.detect_batch(pair)
+        for g, w_ in zip(got, want):
+            np.testing.assert_array_equal(g[0], w_[0])
+
+
 def test_demo_pb_frozen_graph_path_equals_checkpoint_path(weights, tmp_path, monkeypatch):
     """ctpn/demo_pb.py (demo_pb.py:55-98 of the reference): weights from a frozen GraphDef, head tensors fetched by graph name,
     proposal_layer called directly, TextDetector, res file -- the same result file as ctpn/demo.py's ctpn() on that image."""

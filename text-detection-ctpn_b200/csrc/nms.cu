@@ -65,6 +65,7 @@ nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ counts, in
   __shared__ u64 diag[kNmsTile];
   __shared__ u64 s_kept;
   __shared__ int s_nkeep;
+  __shared__ int s_rows[kNmsTile];     // in-block indices of the boxes kept in the current block
   const int img = blockIdx.x, tid = threadIdx.x;
   const int n = counts ? min(counts[img], max_n) : max_n;
   const int cb = (n + kNmsTile - 1) / kNmsTile;
@@ -86,6 +87,7 @@ nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ counts, in
       const int lim = min(kNmsTile, n - base);
       for (int t = 0; t < lim; ++t) {
         if (!((cur >> t) & 1ULL)) {
+          s_rows[__popcll(kept)] = t;
           kept |= 1ULL << t;
           if (nk < keep_stride) keep[nk] = base + t;
           ++nk;
@@ -100,12 +102,19 @@ nms_scan_kernel(const u64 *__restrict__ mask, const int *__restrict__ counts, in
     const u64 kept = s_kept;
     if (max_keep > 0 && s_nkeep >= max_keep) break;
     if (kept) {
+      // OR the mask rows of this block's kept boxes into the suppression words of the later blocks.  The row list is
+      // walked eight at a time with the loads issued before any is consumed: one dependent load per kept box (the
+      // earlier form) exposed a full L2 latency per box, ~0.3 us x 10 000 kept boxes.
+      const int cnt = __popcll(kept);
       for (int j = blk + 1 + tid; j < cb; j += blockDim.x) {
-        u64 acc = remv[j], k = kept;
-        while (k) {
-          int t = __ffsll((long long)k) - 1;
-          k &= k - 1;
-          acc |= m[(size_t)(base + t) * col_blocks + j];
+        u64 acc = remv[j];
+        const u64 *col = m + (size_t)base * col_blocks + j;
+        for (int i = 0; i < cnt; i += 8) {
+          u64 v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = (i + q < cnt) ? col[(size_t)s_rows[i + q] * col_blocks] : 0ULL;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc |= v[q];
         }
         remv[j] = acc;
       }

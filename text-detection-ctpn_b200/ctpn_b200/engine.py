@@ -29,9 +29,14 @@ DEFAULT_CFG = dict(RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=1000, RPN_NMS_THR
 class Engine:
     MODES = {"bf16": 1, "bf16x2": 2, "bf16x3": 3, "f16f8": 4}
 
-    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False, streams=1, mode=None):
+    def __init__(self, weights=None, planes=2, device=0, cfg=None, conv_simt=False, keep_activations=False, streams=1, mode=None,
+                 graph_max_batch=4):
+        """graph_max_batch: batches of up to this many images run as a replayed CUDA graph per (shape, dtype) bucket (the ~25
+        kernel launches of a step cost more than the kernels themselves at batch 1); 0 disables graphs."""
         if mode is not None:
             planes = self.MODES[mode]
+        self.graph_max_batch = int(graph_max_batch)
+        self._graphs = {}
         if not torch.cuda.is_available():
             raise N.CtpnError("ctpn_b200.Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -169,7 +174,7 @@ class Engine:
         count = tail.view(torch.int32) if torch.is_tensor(tail) else tail.view(np.int32)
         return rois, count
 
-    def detect_packed(self, images, im_info):
+    def detect_packed(self, images, im_info, ws_tag=""):
         """images: CUDA [B,H,W,3] uint8/float32; im_info: [B,3] tensor (blob_h, blob_w, scale).
         Returns ONE float32 device buffer [B*post*5 + B]: the rois of all images followed by the int32 counts
         (bit pattern), so that the D2H / the multi-GPU gather of a batch's results is a single transfer."""
@@ -179,8 +184,8 @@ class Engine:
         rois, count = self.unpack(packed, B, rows)
         n = min(self.streams, B)
         if n <= 1:
-            cls, bbox = self.forward_heads(images)
-            self.proposals(cls, bbox, im_info, cls_is_logit=True, out=(rois, count))
+            cls, bbox = self.forward_heads(images, ws_key="net" + ws_tag)
+            self.proposals(cls, bbox, im_info, cls_is_logit=True, ws_key="prop" + ws_tag, out=(rois, count))
             return packed
         # sub-batches on side streams: the SIMT kernels of one sub-batch (conv1_1, BiLSTM, sort, NMS) run beside
         # the tensor-core kernels of the other (a persistent conv CTA leaves room for them on every SM)
@@ -199,6 +204,37 @@ class Engine:
         for st in self._side[:n]:
             main.wait_stream(st)
         return packed
+
+    def detect_packed_graphed(self, images, im_info):
+        """detect_packed through a CUDA graph captured once per (shape, dtype) bucket: inputs are copied into the graph's
+        static buffers, the whole kernel sequence (conv stack, BiLSTM, heads, proposal layer) is replayed with one launch,
+        and the result is the graph's static packed buffer (valid until the next call for the same bucket).  Used for small
+        batches, where launch overhead dominates; the first two calls of a bucket run eagerly (weight upload, F16F8
+        calibration, attribute / tensor-map caches must be warm before a capture)."""
+        key = (tuple(images.shape), images.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = {"calls": 0}
+        if "graph" not in g:
+            g["calls"] += 1
+            if g["calls"] <= 2 or self.streams > 1:
+                return self.detect_packed(images, im_info)
+            g["in"] = torch.empty_like(images)
+            g["info"] = torch.empty((images.shape[0], 3), dtype=torch.float32, device=self.device)
+            g["in"].copy_(images)
+            g["info"].copy_(im_info)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            tag = "/graph%d" % len([1 for v in self._graphs.values() if "graph" in v])
+            self.detect_packed(g["in"], g["info"], ws_tag=tag)      # allocates this bucket's OWN workspaces (never resized or
+            torch.cuda.current_stream().synchronize()               # shared: the graph holds their addresses)
+            with torch.cuda.graph(graph):
+                g["out"] = self.detect_packed(g["in"], g["info"], ws_tag=tag)
+            g["graph"] = graph
+        g["in"].copy_(images, non_blocking=True)
+        g["info"].copy_(im_info, non_blocking=True)
+        g["graph"].replay()
+        return g["out"]
 
     def detect_device(self, images, im_info):
         """As detect_packed; returns device tensors (rois [B,post,5], count [B]) -- views of the packed buffer."""
@@ -254,7 +290,11 @@ class Engine:
         info_h = self._pin("info", (B, 3), torch.float32)
         info_h.numpy()[...] = np.asarray(im_info, np.float32).reshape(B, 3)
         dev = stage.to(self.device, non_blocking=True)
-        packed = self.detect_packed(dev, info_h.to(self.device, non_blocking=True))
+        info_d = info_h.to(self.device, non_blocking=True)
+        if 0 < B <= self.graph_max_batch and not gather:
+            packed = self.detect_packed_graphed(dev, info_d)
+        else:
+            packed = self.detect_packed(dev, info_d)
         if gather:
             from .dist import gather_packed
             packed = gather_packed(packed)
