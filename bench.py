@@ -327,28 +327,29 @@ def main():
     post = eng.result_rows()
 
     gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    inflight = []            # (packed, gathered) of the steps whose all-gather may still be running
+    inflight = []            # (packed, gathered, work) of every step of the current region: released only after the region
 
     def step_device():
         outs = [eng.detect_packed(im, info) for im, info in zip(images, infos)]
         if world > 1:
-            # the one collective of the path: all-gather of this step's packed results, issued on a side stream behind an
-            # event of the compute stream so that it overlaps the next step (drained before the timed region closes)
-            from ctpn_b200.dist import gather_packed
+            # the one collective of the path: all-gather of this step's packed results, issued asynchronously on a side stream
+            # behind an event of the compute stream so that it overlaps the next step (drained before the timed region closes;
+            # measured on 2 GPUs, tools/dbg_gather.py: +0.6 ms/step, a blocking gather on the compute stream +1.0 ms/step)
             packed = torch.cat(outs) if len(outs) > 1 else outs[0]
             done = torch.cuda.Event()
             done.record(torch.cuda.current_stream())
             with torch.cuda.stream(gather_stream):
                 gather_stream.wait_event(done)
-                gathered = gather_packed(packed)
-            inflight.append((packed, gathered))
-            if len(inflight) > 4:
-                inflight.pop(0)
+                gathered = torch.empty((world * packed.numel(),), dtype=packed.dtype, device=dev)
+                work = dist.all_gather_into_tensor(gathered, packed, async_op=True)
+            inflight.append((packed, gathered, work))
             outs = [gathered]
         return outs
 
     def drain():
         if gather_stream is not None:
+            for _p, _g, work in inflight:
+                work.wait()
             torch.cuda.current_stream().wait_stream(gather_stream)
 
     def barrier():
@@ -382,9 +383,15 @@ def main():
     W_ = max(a.warmup, 3)
     for _ in range(W_):
         step_device()
+    drain()
+    del inflight[:]
     sampler = ClockSampler(local) if rank == 0 else None
     # ---- value: device-resident inputs, CUDA events ----
-    N.check(N.lib.ctpn_prof_enable(1), "prof")
+    # per-kernel CUDA events (ctpn_prof_*): inside the timed region at N = 1; at N > 1 they perturb the overlap of the all-gather
+    # with the next step (measured: -2 % at 2 GPUs), so the timed region runs without them and the per-kernel figures of the
+    # roofline come from a separate K-step region right after it
+    prof_inside = world == 1
+    N.check(N.lib.ctpn_prof_enable(1 if prof_inside else 0), "prof")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -394,6 +401,14 @@ def main():
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    del inflight[:]
+    if not prof_inside:
+        N.check(N.lib.ctpn_prof_enable(1), "prof")
+        for _ in range(K):
+            step_device()
+        drain()
+        barrier()
+        del inflight[:]
     prof = N.prof_report()
     N.check(N.lib.ctpn_prof_enable(0), "prof")
     value = world * B * K / (ms / 1e3)
@@ -505,6 +520,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d tcgen05 3x3 conv launches per step)" % (len(conv) and int(sum(p["launches"] for p in conv)) // K),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                          "traffic_note": traffic_note, "peak_source": peak_src + " bf16_tflops_sustained", "ms_per_step": conv_ms,
+                         "measured_in": "the timed region" if world == 1 else "a separate %d-step region after the timed one (per-kernel events perturb the all-gather overlap at N > 1)" % K,
                          "units_per_mac": M["units"], "executed_mma_tflops_bf16_equivalent": achieved * M["units"],
                          "note": "achieved = algorithmic conv FLOPs (%.2f GFLOP/step) / CUDA-event time of the conv launches; in mode %s "
                                  "each algorithmic MAC costs %.1f bf16-rate MMA units" % (alg_flops / 1e9, mode, M["units"])},

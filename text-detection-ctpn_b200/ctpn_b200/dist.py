@@ -15,11 +15,14 @@ def shard_range(n_images, rank, world):
 def gather_packed(packed):
     """packed: this rank's result buffer [L] float32 (rois followed by the int32 counts' bit patterns, see
     Engine.detect_packed) -> [world, L] in rank order.  ONE collective per batch.  Issued on the caller's current
-    stream (Engine.rois_batches calls it on its result stream, off the compute stream)."""
+    stream (Engine.rois_batches calls it on its result stream, off the compute stream).  The collective is enqueued
+    asynchronously and the CURRENT STREAM is made to wait for it (no host block: the synchronous form was seen to hold
+    the host for up to 10 ms per call on 2 GPUs, tools/dbg_gather.py)."""
     world = dist.get_world_size()
     packed = packed.contiguous()
     out = torch.empty((world * packed.numel(),), dtype=packed.dtype, device=packed.device)   # flat: gloo wants [world * L]
-    dist.all_gather_into_tensor(out, packed.reshape(-1))
+    work = dist.all_gather_into_tensor(out, packed.reshape(-1), async_op=True)
+    work.wait()        # NCCL: stream-level wait on the current stream; gloo (CPU tests): blocks until done
     return out.view((world,) + tuple(packed.shape))
 
 
