@@ -168,6 +168,27 @@ def test_f16f8_batch_equals_singles_row_stacked_maps(weights, h, w, n):
         assert torch.equal(c1[0], cls_b[i]) and torch.equal(b1[0], box_b[i])
 
 
+def test_f16f8_recalibration_and_graph_invalidation(weights):
+    """F16F8 activation scales are frozen after the first batch; recalibrate() re-derives them from the next one and drops the
+    captured CUDA graphs (they hold the old scales as kernel arguments): an engine calibrated on a flat grey image (the demo's
+    warm-up) and then recalibrated must give exactly what a fresh engine gives on that image."""
+    from ctpn_b200 import Engine
+    grey = 128 * np.ones((300, 300, 3), np.uint8)
+    im = synth.make_image(33, 300, 300)
+    eng = Engine(weights, mode="f16f8")
+    for _ in range(4):                              # warm-up as ctpn/demo.py: calibrates on the grey image, captures a graph
+        eng.detect(grey)
+    stale = eng.detect(im)[0]
+    eng.recalibrate()
+    assert not eng._graphs
+    got = [eng.detect(im) for _ in range(4)]        # eager, eager, capture + replay, replay
+    want = Engine(weights, mode="f16f8").detect(im)
+    for s_, b_ in got:
+        np.testing.assert_array_equal(s_, want[0])
+        np.testing.assert_array_equal(b_, want[1])
+    print("scores with scales from the grey image differ from the recalibrated ones by %.2e" % float(np.abs(stale[:50] - want[0][:50]).max()))
+
+
 def test_small_batches_replay_a_cuda_graph_per_shape_bucket(weights):
     """Batches of <= graph_max_batch images run as a CUDA graph captured on the third call of a (shape, dtype) bucket; the
     replayed results must equal the eager ones bit for bit, also when two buckets alternate and inputs change between calls."""

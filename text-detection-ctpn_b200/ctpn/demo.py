@@ -78,7 +78,7 @@ def main(argv=None):
     ap.add_argument("--weights", default=None,
                     help="TF checkpoint prefix / directory, frozen .pb, VGG .npy or .npz (default: cfg.TEST.checkpoints_path, "
                          "like demo.py:88-90)")
-    ap.add_argument("--planes", type=int, default=2)
+    ap.add_argument("--planes", type=int, default=2, help="conv arithmetic: 1-3 bf16 planes, 4 = F16F8 (2 tensor-core units per MAC)")
     ap.add_argument("--images", default=os.path.join(cfg.DATA_DIR, 'demo', '*'))
     ap.add_argument("--cfg", default=os.path.join(_PKG, 'ctpn', 'text.yml'))
     ap.add_argument("--native-connector", action="store_true",
@@ -104,6 +104,8 @@ def main(argv=None):
     im = 128 * np.ones((300, 300, 3), dtype=np.uint8)
     for _ in range(2):                                  # warm-up as demo.py:95-97
         test_ctpn(sess, net, im)
+    if args.planes == 4:                                # F16F8: take the activation scales from the first real image, not from the flat
+        sess.engine.recalibrate()                       # grey warm-up image
     for im_name in sorted(glob.glob(args.images)):
         print('~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~')
         print('Demo for {:s}'.format(im_name))

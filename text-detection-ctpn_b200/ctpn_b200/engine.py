@@ -74,6 +74,7 @@ class Engine:
         load_weight_file: TF checkpoint (prefix or directory), frozen .pb, VGG16 .npy dict, .npz."""
         if isinstance(weights, str):
             weights = load_weight_file(weights)
+        self._graphs.clear()          # captured graphs hold the old weight buffers' addresses
         for name, arr in weights.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             N.check(N.lib.ctpn_net_set_weight(self._net, name.encode(), N.ptr(a), a.size), "ctpn_net_set_weight(%s)" % name)
@@ -121,8 +122,12 @@ class Engine:
         return cls, bbox
 
     def recalibrate(self):
-        """F16F8 mode: derive the activation scales again from the next batch (they are frozen after the first one)."""
+        """F16F8 mode: derive the activation scales again from the next batch (they are frozen after the first one).
+        The scales put each layer's calibration maximum two binades below e4m3 saturation; activations beyond that saturate
+        in the e4m3 copies only (those elements fall back to fp16 accuracy), so calibrate on representative images -- not on
+        a flat warm-up image -- and call this again when the input distribution changes."""
         N.check(N.lib.ctpn_net_set_option(self._net, b"recalibrate", 1), "set_option")
+        self._graphs.clear()          # captured graphs hold the old scales as kernel arguments
 
     def tap(self, name):
         """Debug: float32 copy of a named activation of the last forward (keep_activations=True)."""
