@@ -400,7 +400,8 @@ class Engine:
     def detect_lines_batches(self, batches, mode="H", im_info=None, workers=8, gather=False, cfg=None):
         """The whole ctpn() call chain (demo.py:55-68 minus file I/O) for a stream of host batches: rois_batches() on the
         GPU, then TextDetector.detect of every image in the library's host connector (ctpn_text_lines_host, which
-        releases the GIL) on a pool of `workers` threads, one batch behind the GPU.  Yields, per batch, a list of
+        releases the GIL) on a pool of `workers` threads, one batch behind the GPU.  With gather=True (multi-GPU) the rois of
+        all ranks are gathered as in rois_batches and every rank runs the connector on its own shard.  Yields, per batch, a list of
         float64 [m,9] text-line arrays (x1,y1,x2,y2,x3,y3,x4,y4,score) in the frame of the blob divided by im_scale."""
         from concurrent.futures import ThreadPoolExecutor
         from .textlines import text_lines
@@ -419,8 +420,15 @@ class Engine:
         pool = getattr(self, "_line_pool", None)
         if pool is None or pool._max_workers != workers:
             pool = self._line_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="ctpn-lines")
+        shard = None
+        if gather:
+            import torch.distributed as dist
+            shard = (dist.get_rank(), dist.get_world_size())
         pending = None
         for k, rois_list in enumerate(self.rois_batches(tracked(), im_info=im_info, gather=gather)):
+            if shard is not None:      # every rank holds all ranks' rois after the gather; each builds the lines of its own shard
+                per = len(rois_list) // shard[1]
+                rois_list = rois_list[shard[0] * per:(shard[0] + 1) * per]
             H, W = shapes[k]
             scale = 1.0 if im_info is None else float(np.asarray(im_info, np.float32).reshape(-1, 3)[0, 2])
             futs = [pool.submit(lines_of, r, (int(round(H / scale)), int(round(W / scale))), scale) for r in rois_list]
