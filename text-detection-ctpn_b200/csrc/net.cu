@@ -187,7 +187,7 @@ static int finalize(ctpn_net *n) {
 }
 
 struct NetLayout {
-  bool stack;           // F16F8: conv4_3's pooled output and conv5_1..conv5_3 outputs are row-stacked ([B][h + 1][w], zero pad rows)
+  bool stack;           // conv4_3's pooled output and conv5_1..conv5_3 outputs are row-stacked ([B][h + 1][w], zero pad rows)
   size_t act[16];       // offsets of the 14 conv outputs + lstm_out + fc_out
   size_t xproj, heads, total;
   int h[15], w[15];     // spatial size of each conv output
@@ -206,7 +206,7 @@ static NetLayout net_layout(const ctpn_net *n, int B, int H, int W) {
   }
   L.fh = h; L.fw = w;
   // stack the 1/16-scale maps when one tall image needs fewer 16-row tiles than B separate ones (37 rows: 76 vs 96 at B = 32)
-  L.stack = n->f16f8 && ((long long)B * (h + 1) + 15) / 16 < (long long)B * ((h + 15) / 16);
+  L.stack = !n->conv_simt && ((long long)B * (h + 1) + 15) / 16 < (long long)B * ((h + 15) / 16);   // (the SIMT reference kernels of the test library know no stacking)
   if (L.stack)
     for (int l = 9; l <= 12; ++l) sizes[l] = (size_t)P * B * (h + 1) * w * kConvs[l].cout * 2;
   const size_t M = (size_t)B * h * w;
@@ -255,13 +255,18 @@ __global__ void f16f8_to_f32_kernel(const __half *__restrict__ hi, const uint8_t
   dst[i] = (__half2float(hi[pix * C + c]) + r) / s;
 }
 
-__global__ void planes_to_f32_kernel(const __nv_bfloat16 *__restrict__ src, long long n, long long plane_stride, int planes,
-                                     float *__restrict__ dst) {
+__global__ void planes_to_f32_kernel(const __nv_bfloat16 *__restrict__ src, long long n, long long plane_stride, int planes, int C,
+                                     int stack_h, int stack_w, float *__restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = __bfloat162float(src[i]);
-  if (planes > 1) v += __bfloat162float(src[i + plane_stride]);
-  if (planes > 2) v += __bfloat162float(src[i + 2 * plane_stride]);
+  long long j = i;
+  if (stack_h) {     // compact element index -> position in the stacked frame [B][stack_h + 1][stack_w][C]
+    const long long pix = i / C, per = (long long)stack_h * stack_w;
+    j = ((pix / per) * (stack_h + 1) * stack_w + pix % per) * C + i % C;
+  }
+  float v = __bfloat162float(src[j]);
+  if (planes > 1) v += __bfloat162float(src[j + plane_stride]);
+  if (planes > 2) v += __bfloat162float(src[j + 2 * plane_stride]);
   dst[i] = v;
 }
 
@@ -430,10 +435,16 @@ extern "C" int ctpn_net_forward(ctpn_net_t *net, const void *images, int src_is_
   int h = H, w = W;
   for (int l = 1; l < 14; ++l) {
     const ConvSpec &s = kConvs[l];
-    const int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0);
+    int flags = CTPN_F_RELU | (s.pool ? CTPN_F_POOL : 0);
+    const bool stacked = L.stack && l >= 9 && l <= 12;
+    if (stacked) flags |= CTPN_F_STACK_OUT;
+    if (L.stack && l >= 10) flags |= CTPN_F_STACK_IN;
+    if (L.stack && l == 9)      // conv4_3 writes only the image rows of its stacked output: the pad rows must be zero
+      CTPN_CUDA(cudaMemsetAsync(ws + L.act[9], 0, (size_t)P * B * (L.h[9] + 1) * L.w[9] * kConvs[9].cout * 2, (cudaStream_t)stream));
     if ((rc = conv3(ws + L.act[l - 1], net->conv_w[l], net->conv_b[l], ws + L.act[l], B, h, w, s.cin, s.cout, 9, P, flags, stream))) return rc;
     h = L.h[l]; w = L.w[l];
-    net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] = Tap{ws + L.act[l], (long long)B * h * w, s.cout, true};
+    net->taps[s.pool ? std::string(s.name) + "+pool" : std::string(s.name)] =
+        Tap{ws + L.act[l], (long long)B * h * w, s.cout, true, 0.f, 0.f, stacked ? h : 0, stacked ? w : 0};
   }
   }
   const int M = B * L.fh * L.fw;
@@ -467,7 +478,9 @@ extern "C" int ctpn_net_debug_tap(ctpn_net_t *net, const char *name, float *out_
                                                                                        t.channels, t.q_s, t.q_t, t.stack_h, t.stack_w, out_f32);
     CTPN_LAUNCH_CHECK();
   } else if (t.planes) {
-    planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)t.ptr, n, n, net->planes, out_f32);
+    const long long stored = t.stack_h ? n / t.stack_h * (t.stack_h + 1) : n;      // elements per plane incl. pad rows
+    planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)t.ptr, n, stored, net->planes, t.channels,
+                                                                                        t.stack_h, t.stack_w, out_f32);
     CTPN_LAUNCH_CHECK();
   } else {
     CTPN_CUDA(cudaMemcpyAsync(out_f32, t.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

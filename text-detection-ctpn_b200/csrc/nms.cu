@@ -15,40 +15,43 @@ namespace ctpn {
 typedef unsigned long long u64;
 constexpr int kNmsTile = 64;
 
-// grid (G, image); 64 threads.  Each CTA walks (row block, column block) pairs of the upper triangle
+// grid G, 64 threads.  Each CTA walks, image after image, the (row block, column block) pairs of the upper triangle
 // with stride G; thread = one row box against the 64 boxes of the column block.
 __global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ counts, int max_n,
+nms_mask_kernel(const float4 *__restrict__ boxes, const int *__restrict__ counts, int batch, int max_n,
                 int col_blocks, float thresh, u64 *__restrict__ mask, const int *__restrict__ gate) {
-  const int img = blockIdx.y;
-  if (gate && gate[img] == 0) return;   // this image is handled by the column-wise path
-  const int n = counts ? min(counts[img], max_n) : max_n;
-  const int nb = (n + kNmsTile - 1) / kNmsTile;
-  const float4 *b = boxes + (size_t)img * max_n;
   __shared__ float4 cbox[kNmsTile];
   __shared__ float carea[kNmsTile];
   const int t = threadIdx.x;
-  for (int pair = blockIdx.x; pair < nb * nb; pair += gridDim.x) {
-    const int rb = pair / nb, cb = pair % nb;
-    if (cb < rb) continue;
-    const int col_size = min(n - cb * kNmsTile, kNmsTile);
-    __syncthreads();
-    if (t < col_size) {
-      float4 v = b[cb * kNmsTile + t];
-      cbox[t] = v;
-      carea[t] = box_area(v);
-    }
-    __syncthreads();
-    const int row = rb * kNmsTile + t;
-    if (row < n) {
-      float4 me = b[row];
-      float sme = box_area(me);
-      u64 bits = 0;
-      int start = (rb == cb) ? t + 1 : 0;
-      for (int i = start; i < col_size; ++i) {
-        if (iou_above(me, sme, cbox[i], carea[i], thresh)) bits |= 1ULL << i;
+  // the grid is one-dimensional and every CTA walks all images: a batch whose images all took the column-wise path (the
+  // usual case inside the proposal layer) costs one gate test per image instead of a grid of empty CTAs per image
+  for (int img = 0; img < batch; ++img) {
+    if (gate && gate[img] == 0) continue;   // this image is handled by the column-wise path
+    const int n = counts ? min(counts[img], max_n) : max_n;
+    const int nb = (n + kNmsTile - 1) / kNmsTile;
+    const float4 *b = boxes + (size_t)img * max_n;
+    for (int pair = blockIdx.x; pair < nb * nb; pair += gridDim.x) {
+      const int rb = pair / nb, cb = pair % nb;
+      if (cb < rb) continue;
+      const int col_size = min(n - cb * kNmsTile, kNmsTile);
+      __syncthreads();
+      if (t < col_size) {
+        float4 v = b[cb * kNmsTile + t];
+        cbox[t] = v;
+        carea[t] = box_area(v);
       }
-      mask[((size_t)img * max_n + row) * col_blocks + cb] = bits;
+      __syncthreads();
+      const int row = rb * kNmsTile + t;
+      if (row < n) {
+        float4 me = b[row];
+        float sme = box_area(me);
+        u64 bits = 0;
+        int start = (rb == cb) ? t + 1 : 0;
+        for (int i = start; i < col_size; ++i) {
+          if (iou_above(me, sme, cbox[i], carea[i], thresh)) bits |= 1ULL << i;
+        }
+        mask[((size_t)img * max_n + row) * col_blocks + cb] = bits;
+      }
     }
   }
 }
@@ -147,9 +150,9 @@ int nms_sorted_launch(const float *boxes, const int *counts, int batch, int max_
   CTPN_REQUIRE(((uintptr_t)boxes & 15) == 0, "ctpn_nms_sorted: boxes must be 16-byte aligned");
   u64 *mask = reinterpret_cast<u64 *>(workspace);
   long long pairs = (long long)cb * cb;
-  dim3 grid((unsigned)(pairs < 148 * 16 ? pairs : 148 * 16), batch);
+  const unsigned grid = (unsigned)(pairs < 148 * 16 ? pairs : 148 * 16);
   ProfScope prof("nms (mask+scan)", 0.0, st);
-  nms_mask_kernel<<<grid, kNmsTile, 0, st>>>(reinterpret_cast<const float4 *>(boxes), counts, max_n, cb, thresh, mask, gate);
+  nms_mask_kernel<<<grid, kNmsTile, 0, st>>>(reinterpret_cast<const float4 *>(boxes), counts, batch, max_n, cb, thresh, mask, gate);
   CTPN_LAUNCH_CHECK();
   size_t smem = (size_t)cb * sizeof(u64);
   CTPN_REQUIRE(smem <= 200 * 1024, "ctpn_nms_sorted: %d boxes exceed the scan kernel's shared memory", max_n);

@@ -8,6 +8,7 @@
 set -u
 out=${1:-gpurun_out/r2p}
 mkdir -p "$out"
+python -c "import bench; print(bench.sources_sha256())" > "$out/sources_sha256.txt"      # what the captures below were taken from
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$out/launches.csv" \
     python bench.py --steps 2 --warmup 1 --cpu-sample 0 --alt-modes 0 > "$out/bench_under_ncu.log" 2>&1
 for m in f16f8:40 bf16x2:16; do

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--mode", default="f16f8")
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--sha-file", default="", help="sources_sha256.txt written on the box by tools/capture_profiles.sh (default: hash the local tree)")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.csv)))
     i0 = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -45,7 +46,7 @@ def main():
                          "dram_write": to_bytes(r[wr], units[wr]), "time": r[tm] + " " + units[tm]})
     out = {"config": a.config, "mode": a.mode, "batch": a.batch, "launches": len(launches),
            "dram_bytes_per_step": sum(l["dram_read"] + l["dram_write"] for l in launches),
-           "per_launch": launches, "sources_sha256": sources_sha256(),
+           "per_launch": launches, "sources_sha256": open(a.sha_file).read().strip() if a.sha_file else sources_sha256(),
            "how": "ncu --set full --clock-control none -k regex:conv_tc, one step of tools/ncu_step.py; dram__bytes_read.sum + dram__bytes_write.sum"}
     print(json.dumps(out, indent=1))
 
