@@ -13,12 +13,21 @@
  *                        (called by lib/utils/gpu_nms.pyx:31)
  *   ctpn_nms_sorted      lib/utils/nms_kernel.cu:34-78 (nms_kernel) + :124-139 (host greedy scan)
  *   ctpn_proposals       lib/rpn_msr/proposal_layer_tf.py:14-157 (tf.py_func body, lib/networks/network.py:214)
- *   ctpn_conv1_1_tc / ctpn_conv3x3 (taps=9, optional fused 2x2 max-pool)
+ *   ctpn_conv1_1_tc[_f16f8] / ctpn_conv3x3[_f16f8] (taps=9, optional fused 2x2 max-pool)
  *                        lib/networks/network.py:160-183 (conv), :189-196 (max_pool)
  *   ctpn_bilstm_recurrent, ctpn_conv3x3 (taps=1: x-projection, FC and head matmuls)
  *                        lib/networks/network.py:88-113 (Bilstm), :144-158 (lstm_fc)
  *   ctpn_net_forward     lib/networks/VGGnet_test.py:16-52 up to the two head tensors
  *                        (the demo_pb.py:73-75 boundary), fed by lib/fast_rcnn/test.py:7-31
+ *   ctpn_resize_linear_u8   cv2.resize in resize_im, ctpn/demo.py:21-25 (and draw_boxes :50)
+ *   ctpn_image_blob_f32     _get_image_blob, lib/fast_rcnn/test.py:7-31 (float32 cv2.resize of the mean-subtracted image)
+ *   ctpn_text_filter_nms_host / ctpn_text_groups_host / ctpn_text_lines_host
+ *                        TextDetector.detect, lib/text_connector/detectors.py:19-49; graph builder
+ *                        text_proposal_graph_builder.py:6-78; chains other.py:16-29; line fitting
+ *                        text_proposal_connector.py:21-64 and text_proposal_connector_oriented.py:24-105
+ *   ctpn_crc32c_host     the per-tensor checksum of the TF checkpoints the reference restores (ctpn/demo.py:88-90)
+ * Test-only entry points (float32 SIMT reference kernels, hardware probes) and every ablation / tuning switch are NOT in
+ * this library: they live in tests/_native/libctpn_b200_dbg.so (csrc/testing/ctpn_b200_testing.h).
  */
 #ifndef CTPN_B200_H_
 #define CTPN_B200_H_
