@@ -167,7 +167,10 @@ class Engine:
 
     # ---- public API ------------------------------------------------------------------------
     def result_rows(self):
-        return int(self.cfg["RPN_POST_NMS_TOP_N"])
+        rows = int(self.cfg["RPN_POST_NMS_TOP_N"])
+        if rows <= 0:
+            raise ValueError("the packed result path needs RPN_POST_NMS_TOP_N > 0 (use Engine.proposals for an uncapped proposal list)")
+        return rows
 
     @staticmethod
     def unpack(packed, B, rows):
