@@ -65,8 +65,11 @@ def conv_stack(blob, weights, mode, acc=torch.float64):
             if mode != "f16x1":
                 a1 = (x - a0).float().to(acc)
                 w1 = (w - w0).float().to(acc)
-                q = {"f16f8": e4m3, "f16f8h": e4m3_head, "f16x2": lambda t: f16(t.float()).to(acc)}[mode]
-                y = y + F.conv2d(q(a0), q(w1), None, padding=1) + F.conv2d(q(a1), q(w0), None, padding=1)
+                if mode == "f16f8_25":       # 2.5 units: a * r_w exactly on fp16 operands (1 unit), r_a * w on e4m3 copies (1/2 unit)
+                    y = y + F.conv2d(a0, f16(w1.float()).to(acc), None, padding=1) + F.conv2d(e4m3_head(a1), e4m3_head(w0), None, padding=1)
+                else:
+                    q = {"f16f8": e4m3, "f16f8h": e4m3_head, "f16x2": lambda t: f16(t.float()).to(acc)}[mode]
+                    y = y + F.conv2d(q(a0), q(w1), None, padding=1) + F.conv2d(q(a1), q(w0), None, padding=1)
         else:
             a0 = bf16(x.float()).to(acc)
             w0 = bf16(w.float()).to(acc)
@@ -98,7 +101,7 @@ def main():
     ap.add_argument("--height", type=int, default=600)
     ap.add_argument("--width", type=int, default=900)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--modes", default="bf16x1,bf16x2,fp8cross,f16x1,f16f8,f16f8h,f16x2")
+    ap.add_argument("--modes", default="bf16x1,bf16x2,fp8cross,f16x1,f16f8,f16f8h,f16f8_25,f16x2")
     a = ap.parse_args()
     torch.set_num_threads(min(32, os.cpu_count() or 1))
     w = synth.make_weights(0)
