@@ -168,6 +168,24 @@ def test_f16f8_batch_equals_singles_row_stacked_maps(weights, h, w, n):
         assert torch.equal(c1[0], cls_b[i]) and torch.equal(b1[0], box_b[i])
 
 
+def test_streaming_api_with_large_distinct_unpinned_batches(weights):
+    """rois_batches stages ndarray / unpinned batches through pinned buffers while the previous batch's H2D may
+    still be in flight.  Four distinct 13 MB ndarray batches (H2D ~ 1 ms each): every streamed result must equal the
+    one-batch-at-a-time result, i.e. no batch may see pixels of its successor."""
+    from ctpn_b200 import Engine
+    eng = Engine(weights, planes=1)
+    rs = np.random.RandomState(5)
+    batches = [rs.randint(0, 256, size=(8, 600, 900, 3), dtype=np.uint8) for _ in range(4)]
+    want = [eng.rois_batch(b) for b in batches]
+    got = list(eng.rois_batches(iter(batches)))
+    got_again = list(eng.rois_batches(torch.from_numpy(b) for b in batches))      # unpinned CPU tensors take the same route
+    assert len(got) == len(got_again) == 4
+    for k in range(4):
+        for i in range(8):
+            np.testing.assert_array_equal(got[k][i], want[k][i])
+            np.testing.assert_array_equal(got_again[k][i], want[k][i])
+
+
 def test_f16f8_recalibration_and_graph_invalidation(weights):
     """F16F8 activation scales are frozen after the first batch; recalibrate() re-derives them from the next one and drops the
     captured CUDA graphs (they hold the old scales as kernel arguments): an engine calibrated on a flat grey image (the demo's
