@@ -87,21 +87,14 @@ def cmd_conv(a):
 
 
 def _pow2_floor(v):
-    return float(2.0 ** np.floor(np.log2(v)))
+    from oracle import quant
+    return quant.pow2_floor(v)
 
 
 def f16f8_quantize(x, s, t):
-    """float32 tensor [..., C] (C % 64 == 0) -> (fp16 plane, uint8 cross plane [..., C/64, 128], dequantised (h, v8, r8) as
-    float64) under the F16F8 rules of csrc/common.cuh: h = fp16(x s), v8 = e4m3(x t), r8 = e4m3((x s - h) 2^11 t / s)."""
-    import torch
-    h = (x * s).to(torch.float16)
-    r = x * s - h.float()
-    v8 = (x * t).clamp(-448, 448).to(torch.float8_e4m3fn)
-    r8 = (r * (2048.0 * t / s)).clamp(-448, 448).to(torch.float8_e4m3fn)
-    lead = x.shape[:-1]
-    C = x.shape[-1]
-    cross = torch.cat([v8.view(torch.uint8).reshape(lead + (C // 64, 64)), r8.view(torch.uint8).reshape(lead + (C // 64, 64))], dim=-1)
-    return h, cross.contiguous(), (h.double() / s, v8.double() / t, r8.double() / (2048.0 * t))
+    """The F16F8 operand format (csrc/common.cuh) as restated on the CPU in oracle/quant.py."""
+    from oracle import quant
+    return quant.quantize(x, s, t)
 
 
 def cmd_conv_f16f8(a):
