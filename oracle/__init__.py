@@ -14,6 +14,13 @@ Pinning status (see DESIGN.md "Oracle"):
   * network half (VGG16 / BiLSTM / heads / softmax): PARITY UNPINNED.  The
     arithmetic lives in TensorFlow 1.3 (requirements.txt:2), which is neither
     vendored nor installable here; ``net_cpu.py`` restates the documented
-    TF 1.3 semantics on torch-CPU and is cross-checked only against an
-    independent float64 evaluation of itself.
+    TF 1.3 semantics on torch-CPU.  Narrowed, not closed: ``net_alt.py`` is a
+    second, independently written restatement (numpy im2col convolutions,
+    torch.nn.LSTM with permuted gate columns) and tests/test_oracle_net_cpu.py
+    asserts the two agree to 1e-11 in float64.
+  * image front-end (``resize.py``): uint8 INTER_LINEAR PINNED against
+    cv2.resize; float32 INTER_LINEAR PINNED against OpenCV's own code path
+    (cv2 with IPP disabled; IPP-dispatching builds differ, see the docstring).
+  * ``quant.py``: this repo's own F16F8 operand format (no counterpart in the
+    reference), checked against torch's float16 / float8_e4m3fn conversions.
 """

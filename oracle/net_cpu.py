@@ -2,7 +2,8 @@
 graph (VGG16 -> rpn_conv -> BiLSTM -> FC -> heads -> pair softmax).
 Not imported by the product.  PARITY UNPINNED: TensorFlow 1.3 is not available
 (requirements.txt:2), so this restates TF 1.3's documented op semantics; it is
-checked only against a float64 evaluation of itself.
+checked against a float64 evaluation of itself and against oracle/net_alt.py, an
+independently written second restatement (tests/test_oracle_net_cpu.py).
 
 Follows (paths relative to /root/reference):
   topology            lib/networks/VGGnet_test.py:16-55
