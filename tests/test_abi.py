@@ -3,6 +3,8 @@ the ctypes table in ctpn_b200/_native.py covers exactly the header."""
 import os
 import re
 
+import pytest
+
 from ctpn_b200 import _native as N
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -63,3 +65,35 @@ def test_invalid_arguments_are_reported_not_crashed():
     assert N.lib.ctpn_net_feature_hw(1200, 1600, C.byref(fh), C.byref(fw)) == 0 and (fh.value, fw.value) == (75, 100)
     assert N.lib.ctpn_conv3x3(None, None, None, None, 1, 8, 8, 64, 64, 9, 1, 0, None) == 1
     assert N.lib.ctpn_nms_workspace_bytes(1, 12000) == 12000 * 188 * 8
+
+
+def test_product_refuses_to_run_without_a_gpu_or_without_the_library():
+    """No CPU fallback anywhere on the product path: without a CUDA device the engine raises and device entry
+    points return CTPN_ERR_NO_DEVICE; without the shared library the package does not import."""
+    import ctypes as C
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less build container")
+    from ctpn_b200 import CtpnError, Engine
+    with pytest.raises(CtpnError, match="no CPU fallback"):
+        Engine(None)
+    keep, num, boxes = (C.c_int * 4)(), C.c_int(), (C.c_float * 20)()
+    assert N.lib.ctpn_nms_host(keep, C.byref(num), boxes, 4, 5, 0.7, 0) == N.ERR_NO_DEVICE
+    with pytest.raises(CtpnError):
+        N.check(N.lib.ctpn_device_ok(0), "ctpn_device_ok")
+    # a package copy without the .so must fail at import, not fall back
+    code = ("import sys, os, shutil, tempfile\n"
+            "d = tempfile.mkdtemp()\n"
+            "shutil.copytree(%r, os.path.join(d, 'ctpn_b200'), ignore=shutil.ignore_patterns('*.so', '__pycache__'))\n"
+            "sys.path.insert(0, d)\n"
+            "try:\n"
+            "    import ctpn_b200\n"
+            "except ImportError as e:\n"
+            "    assert 'no CPU fallback' in str(e), e\n"
+            "    print('refused')\n"
+            "finally:\n"
+            "    shutil.rmtree(d)\n") % os.path.dirname(N.__file__)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.stdout.strip() == "refused", out.stdout + out.stderr
