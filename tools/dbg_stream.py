@@ -1,5 +1,12 @@
-import sys, os
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/text-detection-ctpn_b200')
+#!/usr/bin/env python
+"""GPU experiment that located the cross-stream allocator race of Engine.rois_batches (a buffer allocated on the copy stream
+aliasing memory the compute stream was still reading; fixed in engine.py, regression test
+tests/test_net_gpu.py::test_streaming_api_with_large_distinct_unpinned_batches): streamed batches must equal the same batches run one by one."""
+import os
+import sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "text-detection-ctpn_b200"))
 import numpy as np, torch
 from oracle import synth
 from ctpn_b200 import Engine

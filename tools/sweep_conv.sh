@@ -1,3 +1,5 @@
+#!/bin/bash
+# Run ON THE GPU BOX: the per-layer conv timings / ablations behind profiles/r2_conv_ablation.txt (debug library switches).
 python tools/time_conv.py --mode f16f8
 CTPN_TC_STAGE_SMALL=0 python tools/time_conv.py --mode f16f8
 python tools/time_conv.py --mode f16f8 --H 150 --W 225 --cin 256 --cout 256
