@@ -121,3 +121,30 @@ def make_text_proposals(seed, im_h=600, im_w=900, n_lines=6, n_noise=120):
     s = s + (np.arange(s.size, dtype=np.float32) * np.float32(1e-6))
     order = np.argsort(-s, kind="stable")
     return b[order], s[order][:, None].astype(np.float32)
+
+
+def make_gt_boxes(seed, im_h=600, im_w=900, n_lines=6, scale=1.0, n_dontcare=0, hard_frac=0.0, n_outside=0):
+    """Training annotations shaped like the reference's split text lines (prepare_training_data/split_label.py): 16-px
+    wide ground-truth strips along a few lines, multiplied by the image scale (so coordinates are fractional), class 1.
+    Returns gt_boxes [G,5] float32, gt_ishard [G] int32, dontcare_areas [D,4] float32."""
+    rs = np.random.RandomState(6000 + seed)
+    gt = []
+    for _ in range(n_lines):
+        c0 = rs.randint(0, max(1, int(im_w / scale) // 16 - 6))
+        c1 = rs.randint(c0 + 2, min(c0 + 30, int(im_w / scale) // 16) + 1)
+        yc = rs.uniform(30, im_h / scale - 30)
+        hh = rs.uniform(10, 60)
+        slope = rs.uniform(-0.05, 0.05)
+        for c in range(c0, c1):
+            y = yc + slope * 16 * (c - c0)
+            gt.append([16 * c, max(0.0, y - hh / 2), 16 * c + 15, min(im_h / scale - 1, y + hh / 2), 1.0])
+    for _ in range(n_outside):          # annotations that fall off the resized image: no inside anchor touches them
+        gt.append([im_w / scale + 40, 10, im_w / scale + 55, 40, 1.0])
+    gt = np.asarray(gt, np.float32)
+    gt[:, :4] *= np.float32(scale)
+    hard = (rs.rand(gt.shape[0]) < hard_frac).astype(np.int32)
+    dc = np.zeros((n_dontcare, 4), np.float32)
+    for i in range(n_dontcare):
+        x, y = rs.uniform(0, im_w - 120), rs.uniform(0, im_h - 80)
+        dc[i] = [x, y, x + rs.uniform(30, 110), y + rs.uniform(20, 70)]
+    return gt, hard, dc
