@@ -25,6 +25,9 @@
  *                        TextDetector.detect, lib/text_connector/detectors.py:19-49; graph builder
  *                        text_proposal_graph_builder.py:6-78; chains other.py:16-29; line fitting
  *                        text_proposal_connector.py:21-64 and text_proposal_connector_oriented.py:24-105
+ *   ctpn_bbox_overlaps_host / ctpn_bbox_intersections_host   lib/utils/bbox.pyx:15-55, :57-95 (Cython, CPU)
+ *   ctpn_anchor_targets_host   lib/rpn_msr/anchor_target_layer_tf.py:78-175, :201 (tf.py_func body, network.py:199-212;
+ *                        training only -- host code, as the reference's is)
  *   ctpn_crc32c_host     the per-tensor checksum of the TF checkpoints the reference restores (ctpn/demo.py:88-90)
  * Test-only entry points (float32 SIMT reference kernels, hardware probes) and every ablation / tuning switch are NOT in
  * this library: they live in tests/_native/libctpn_b200_dbg.so (csrc/testing/ctpn_b200_testing.h).
@@ -216,6 +219,27 @@ int ctpn_text_filter_nms_host(const float *proposals, const float *scores, int n
                               int *num_keep);
 int ctpn_text_groups_host(const float *proposals, const float *scores, int m, int im_w, const float *cfg9, int *offsets,
                           int *members, int members_capacity, int *num_groups, int *num_members);
+
+/* ---- RPN training targets (host) -------------------------------------------------------------
+ * The reference computes these on the CPU once per training image; so does this library (plain C++, no device work).
+ * ctpn_bbox_overlaps_host: lib/utils/bbox.pyx:15-55 -- IoU with the +1 pixel convention of boxes [n][boxes_stride>=4]
+ * against query_boxes [k][query_stride>=4] (x1,y1,x2,y2 in the first four columns), float64, overlaps [n][k]; 0 where
+ * disjoint.  ctpn_bbox_intersections_host: bbox.pyx:57-95 -- intersection / area(query box). */
+int ctpn_bbox_overlaps_host(const double *boxes, int n, int boxes_stride, const double *query_boxes, int k, int query_stride,
+                            double *overlaps);
+int ctpn_bbox_intersections_host(const double *boxes, int n, int boxes_stride, const double *query_boxes, int k,
+                                 int query_stride, double *intersections);
+/* anchor_target_layer_tf.py:78-175 and :201 fused: labels (1 fg, 0 bg, -1 ignored; BEFORE the random sub-sampling of
+ * :181-198, which the caller does so that the random stream stays its own) and float32 regression targets
+ * (bbox_transform.py:10-29 against each anchor's best ground truth) for all feat_h*feat_w*10 anchors in (row, col, anchor)
+ * order; anchors outside the im_w x im_h image get label -1 and zero targets (_unmap, :256-267).
+ * gt_boxes [num_gt][4] float64 (num_gt >= 1); gt_is_f32 != 0 when the caller's annotations were float32 (numpy then
+ * keeps the ground-truth side of bbox_transform in float32); gt_ishard [num_gt] or NULL; dontcare_areas
+ * [num_dontcare][4] or NULL.  cfg5 = (RPN_NEGATIVE_OVERLAP, RPN_POSITIVE_OVERLAP, RPN_CLOBBER_POSITIVES,
+ * DONTCARE_AREA_INTERSECTION_HI, PRECLUDE_HARD_SAMPLES), lib/fast_rcnn/config.py:112-121. */
+int ctpn_anchor_targets_host(const double *gt_boxes, int num_gt, int gt_is_f32, const unsigned char *gt_ishard,
+                             const double *dontcare_areas, int num_dontcare, int feat_h, int feat_w, int feat_stride,
+                             double im_h, double im_w, const double *cfg5, float *labels, float *bbox_targets);
 
 #ifdef __cplusplus
 }

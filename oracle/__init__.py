@@ -21,6 +21,11 @@ Pinning status (see DESIGN.md "Oracle"):
   * image front-end (``resize.py``): uint8 INTER_LINEAR PINNED against
     cv2.resize; float32 INTER_LINEAR PINNED against OpenCV's own code path
     (cv2 with IPP disabled; IPP-dispatching builds differ, see the docstring).
+  * training-side target ops (``train_targets.py``: bbox_overlaps,
+    bbox_intersections, bbox_transform, anchor_target_layer): PINNED against
+    outputs of the reference's own operator run on its own Cython bbox module
+    (re-cythonized into oracle/_ref by oracle/Makefile),
+    ``tests/golden/make_golden_train.py``.
   * ``quant.py``: this repo's own F16F8 operand format (no counterpart in the
     reference), checked against torch's float16 / float8_e4m3fn conversions.
 """

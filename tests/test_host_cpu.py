@@ -116,3 +116,13 @@ def test_product_and_oracle_synthetic_generators_agree():
     for k in a:
         np.testing.assert_array_equal(a[k], b[k])
     np.testing.assert_array_equal(synthetic.make_image(3, 40, 50), synth.make_image(3, 40, 50))
+
+
+def test_clip_boxes_in_place_x_then_y():
+    from lib.text_connector.other import clip_boxes
+    b = np.array([[-3.0, -2.0, 950.0, 700.0], [10.5, 599.5, 899.5, 20.0], [1, 2, 3, 4, 5, 6, 2000, -7]][:2], np.float32)
+    q = np.array([[1, 2, 3, 4, 5, 6, 2000, -7]], np.float64)             # 8-column quadrilateral rows are clipped the same way
+    out = clip_boxes(b, (600, 900))
+    assert out is b
+    assert np.array_equal(b, np.array([[0, 0, 899, 599], [10.5, 599, 899, 20]], np.float32))
+    assert np.array_equal(clip_boxes(q, (600, 900)), [[1, 2, 3, 4, 5, 6, 899, 0]])

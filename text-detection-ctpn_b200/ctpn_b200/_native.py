@@ -47,6 +47,9 @@ SIGNATURES = {
     "ctpn_text_lines_host": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "ctpn_text_filter_nms_host": (_i, [_p, _p, _i, _p, _p, _p]),
     "ctpn_text_groups_host": (_i, [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "ctpn_bbox_overlaps_host": (_i, [_p, _i, _i, _p, _i, _i, _p]),
+    "ctpn_bbox_intersections_host": (_i, [_p, _i, _i, _p, _i, _i, _p]),
+    "ctpn_anchor_targets_host": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _p, _p]),
     "ctpn_resize_out_size": (_i, [_i, _i, C.c_double, C.c_double, _p, _p]),
     "ctpn_resize_linear_u8": (_i, [_p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _i, _i, _p]),
     "ctpn_image_blob_f32": (_i, [_p, _p, _i, _i, _i, C.c_double, C.c_double, _p, _i, _i, _p]),

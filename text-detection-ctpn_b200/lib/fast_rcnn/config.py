@@ -42,7 +42,8 @@ __C.SUBCLS_NAME = 'voxel_exemplars'
 __C.EXP_DIR = 'default'
 __C.LOG_DIR = 'default'
 
-# text.yml carries a TRAIN block; the keys are accepted (and ignored by this inference engine)
+# text.yml carries a TRAIN block; the keys are accepted.  The inference engine ignores them; the RPN_* / DONTCARE /
+# PRECLUDE keys are read by lib/rpn_msr/anchor_target_layer_tf.py (config.py:112-140)
 __C.TRAIN = edict(dict(
     restore=0, max_steps=100000, SOLVER='Momentum', OHEM=False, RPN_BATCHSIZE=256, BATCH_SIZE=128,
     LOG_IMAGE_ITERS=100, DISPLAY=10, SNAPSHOT_ITERS=5000, HAS_RPN=False, LEARNING_RATE=0.001, MOMENTUM=0.9,
@@ -50,7 +51,8 @@ __C.TRAIN = edict(dict(
     RPN_POSITIVE_OVERLAP=0.7, PROPOSAL_METHOD='selective_search', BG_THRESH_LO=0.1,
     PRECLUDE_HARD_SAMPLES=True, BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0),
     RPN_BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0), RPN_POSITIVE_WEIGHT=-1.0, FG_FRACTION=0.25,
-    WEIGHT_DECAY=0.0005))
+    WEIGHT_DECAY=0.0005, RPN_NEGATIVE_OVERLAP=0.3, RPN_CLOBBER_POSITIVES=False, RPN_FG_FRACTION=0.5,
+    DONTCARE_AREA_INTERSECTION_HI=0.5))
 
 __C.TEST = edict()
 __C.TEST.checkpoints_path = "checkpoints/"

@@ -8,8 +8,10 @@ def threshold(coords, min_, max_):
 
 
 def clip_boxes(boxes, im_shape):
-    boxes[:, 0::2] = threshold(boxes[:, 0::2], 0, im_shape[1] - 1)
-    boxes[:, 1::2] = threshold(boxes[:, 1::2], 0, im_shape[0] - 1)
+    """In place, like the reference: x columns to [0, width-1], then y columns to [0, height-1]."""
+    height, width = im_shape[0], im_shape[1]
+    for first_col, limit in ((0, width - 1), (1, height - 1)):
+        boxes[:, first_col::2] = threshold(boxes[:, first_col::2], 0, limit)
     return boxes
 
 
