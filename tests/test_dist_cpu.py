@@ -1,7 +1,6 @@
 """CPU, world_size 2 over gloo: the multi-GPU host logic (image sharding + the one result gather)."""
 import os
 import socket
-import sys
 
 import numpy as np
 import torch

@@ -2,7 +2,6 @@
 without TensorFlow.  Files are produced by tests/tf_format_writer.py (an independent writer of the same published
 formats; no TF-written file is available offline)."""
 import os
-import struct
 
 import numpy as np
 import pytest

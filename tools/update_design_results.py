@@ -1,6 +1,5 @@
 #!/usr/bin/env python
 """Regenerate the results table of DESIGN.md section 6 from the committed bench lines (profiles/r2_bench_*.json)."""
-import glob
 import os
 import re
 import subprocess
