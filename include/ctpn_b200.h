@@ -26,7 +26,7 @@
  *                        text_proposal_graph_builder.py:6-78; chains other.py:16-29; line fitting
  *                        text_proposal_connector.py:21-64 and text_proposal_connector_oriented.py:24-105
  *   ctpn_bbox_overlaps_host / ctpn_bbox_intersections_host   lib/utils/bbox.pyx:15-55, :57-95 (Cython, CPU)
- *   ctpn_anchor_targets_host   lib/rpn_msr/anchor_target_layer_tf.py:78-175, :201 (tf.py_func body, network.py:199-212;
+ *   ctpn_anchor_targets_host   lib/rpn_msr/anchor_target_layer_tf.py:78-175, :201 (tf.py_func body, network.py:225-243;
  *                        training only -- host code, as the reference's is)
  *   ctpn_crc32c_host     the per-tensor checksum of the TF checkpoints the reference restores (ctpn/demo.py:88-90)
  * Test-only entry points (float32 SIMT reference kernels, hardware probes) and every ablation / tuning switch are NOT in

@@ -1,7 +1,7 @@
 """anchor_target_layer(rpn_cls_score, gt_boxes, gt_ishard, dontcare_areas, im_info, _feat_stride, anchor_scales)
 -> (rpn_labels [1,H,W,A], rpn_bbox_targets, rpn_bbox_inside_weights, rpn_bbox_outside_weights [1,H,W,4A]), float32:
 the operator interface of lib/rpn_msr/anchor_target_layer_tf.py:10 (called through tf.py_func at
-lib/networks/network.py:199-212 in the training graph).  Training is outside this engine's scope; this
+lib/networks/network.py:225-243 in the training graph).  Training is outside this engine's scope; this
 operator exists so that a training loop written against the reference finds it, and it is host code as the reference's is.
 
 Overlaps, label assignment and regression targets come from one native pass (ctpn_anchor_targets_host; no
