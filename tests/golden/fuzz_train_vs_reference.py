@@ -11,10 +11,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
 import make_golden  # noqa: E402
 import make_golden_train  # noqa: E402
-from time_train_targets import load_product_operator  # noqa: E402
+from product_import import load_product_module  # noqa: E402
 
 
 def main(cases):
@@ -22,9 +21,7 @@ def main(cases):
     make_golden_train.load_bbox_module()
     from lib.rpn_msr import anchor_target_layer_tf as ref_layer
     from oracle import synth, train_targets as T
-    ours = load_product_operator(os.path.join(ROOT, "text-detection-ctpn_b200"))
-    from ctpn_b200 import _native  # noqa: F401  (the product's config object is separate from the reference's `cfg`)
-    import importlib
+    ours = load_product_module("lib.rpn_msr.anchor_target_layer_tf").anchor_target_layer
     bad = 0
     stats = dict(fg=0, bg=0, hard=0, dontcare=0, outside=0, f64=0, weighted=0)
     for case in range(cases):
@@ -46,7 +43,6 @@ def main(cases):
         clobber = case % 4 == 0
         cfg.TRAIN.RPN_POSITIVE_WEIGHT, cfg.TRAIN.RPN_CLOBBER_POSITIVES = pw, clobber
         ocfg = dict(T.TRAIN_CFG, RPN_POSITIVE_WEIGHT=pw, RPN_CLOBBER_POSITIVES=clobber)
-        pcfg = sys.modules.get("lib.fast_rcnn.config")
         score = np.zeros((1, H, W, 20), np.float32)
         info = np.array([[ih, iw, scale]], np.float32)
         outs = []

@@ -1,8 +1,8 @@
 """TextDetector (lib/text_connector/detectors.py:19-49) as a delegate to the library's host connector
 (csrc/textline.cu through ctpn_b200/textlines.py).  detect(): score filter > 0.7, score order, NMS 0.2 and the proposal
 graph run in C++; the line fit uses numpy's np.polyfit, so the output equals the reference's bit for bit.
-TextDetector(native=True) also fits in C++ (ctpn_text_lines_host: same lines, correctly rounded coordinates that differ
-from numpy's by <= 1 float32 ulp on exact ties; ~20x faster still)."""
+TextDetector(native=True) also fits in C++ (ctpn_text_lines_host: same lines; the correctly rounded fit differs from
+numpy's by <= 1 float32 ulp on exact ties, <= 2e-4 px in the final coordinates; ~20x faster still)."""
 from ctpn_b200 import textlines
 from lib.fast_rcnn.config import cfg
 from .text_connect_cfg import native_cfg

@@ -40,7 +40,8 @@ def main():
         assert os.path.realpath(ref_layer.__file__).startswith("/root/reference")
     from oracle import synth, train_targets as T
     # the product's operator lives in a package of the same name: load it by path
-    ours = load_product_operator(os.path.join(ROOT, "text-detection-ctpn_b200"))
+    from product_import import load_product_module          # the product's operator lives in a package of the same name
+    ours = load_product_module("lib.rpn_msr.anchor_target_layer_tf").anchor_target_layer
     cpu = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][:1]
     print("host: %s, %s, numpy %s, 1 thread" % (cpu[0] if cpu else platform.processor(), platform.platform(), np.__version__))
     print("%-34s %6s %8s | %12s %12s %12s | %s" % ("case", "gt", "anchors", "reference ms", "oracle ms", "this repo ms", "speed-up vs reference"))
@@ -64,22 +65,6 @@ def main():
         assert all(np.array_equal(a, b) for a, b in zip(outs["oracle"], outs["ours"]))
         print("%-34s %6d %8d | %12s %12.2f %12.3f | %s" % (name, gt.shape[0], H * W * 10, "%.2f" % t_ref if t_ref else "-", t_or, t_us,
                                                         "%.0fx" % (t_ref / t_us) if t_ref else "-"))
-
-
-def load_product_operator(pkg):
-    """Import the product's lib.rpn_msr.anchor_target_layer_tf beside the reference's package of the same name."""
-    import importlib
-    saved = {k: sys.modules.pop(k) for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]}
-    sys.path.insert(0, pkg)
-    try:
-        mod = importlib.import_module("lib.rpn_msr.anchor_target_layer_tf")
-        assert os.path.realpath(mod.__file__).startswith(pkg)
-        return mod.anchor_target_layer
-    finally:
-        sys.path.remove(pkg)
-        for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
-            sys.modules.pop(k)
-        sys.modules.update(saved)
 
 
 if __name__ == "__main__":
