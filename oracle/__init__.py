@@ -17,7 +17,12 @@ Pinning status (see DESIGN.md "Oracle"):
     TF 1.3 semantics on torch-CPU.  Narrowed, not closed: ``net_alt.py`` is a
     second, independently written restatement (numpy im2col convolutions,
     torch.nn.LSTM with permuted gate columns) and tests/test_oracle_net_cpu.py
-    asserts the two agree to 1e-11 in float64.
+    asserts the two agree to 1e-11 in float64.  The graph WIRING is pinned:
+    tests/golden/make_golden_net.py runs the reference's own VGGnet_test /
+    network.py / test_ctpn / py_func proposal layer, unmodified, on a numpy
+    stand-in for the TensorFlow functions they call (tests/golden/tf1_stub),
+    and net_cpu.py + postproc.py match its tensors and proposals to float32
+    rounding; the per-op TF semantics restated in that stub stay unpinned.
   * image front-end (``resize.py``): uint8 INTER_LINEAR PINNED against
     cv2.resize; float32 INTER_LINEAR PINNED against OpenCV's own code path
     (cv2 with IPP disabled; IPP-dispatching builds differ, see the docstring).

@@ -3,7 +3,9 @@ graph (VGG16 -> rpn_conv -> BiLSTM -> FC -> heads -> pair softmax).
 Not imported by the product.  PARITY UNPINNED: TensorFlow 1.3 is not available
 (requirements.txt:2), so this restates TF 1.3's documented op semantics; it is
 checked against a float64 evaluation of itself and against oracle/net_alt.py, an
-independently written second restatement (tests/test_oracle_net_cpu.py).
+independently written second restatement (tests/test_oracle_net_cpu.py).  The graph wiring (layer
+order, variable names, row sequences, reshapes, proposal-layer call) is pinned to the reference's own graph-building code
+run on a numpy TensorFlow stand-in (tests/golden/make_golden_net.py, reference_net_wiring.npz); the per-op semantics are not.
 
 Follows (paths relative to /root/reference):
   topology            lib/networks/VGGnet_test.py:16-55

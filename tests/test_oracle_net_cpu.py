@@ -35,3 +35,46 @@ def test_restatements_agree_on_a_batch_and_reverse_direction_matters():
     w2[net_cpu.LSTM_FW + "/kernel"], w2[net_cpu.LSTM_BW + "/kernel"] = w[net_cpu.LSTM_BW + "/kernel"], w[net_cpu.LSTM_FW + "/kernel"]
     c = net_alt.forward(blob, w2)
     assert np.abs(a["rpn_cls_score"] - c["rpn_cls_score"]).max() > 1e-3
+
+
+# ---- the oracle against the reference's OWN graph code ---------------------------------------------------------------------
+# tests/golden/reference_net_wiring.npz: get_network("VGGnet_test") + test_ctpn + the py_func proposal layer, imported
+# unmodified from /root/reference and executed on tests/golden/tf1_stub (numpy stand-ins for the TensorFlow functions that
+# code calls).  Pins the wiring (layer order, variable names, row sequences, fw/bw concatenation, reshapes, pair softmax,
+# blob / im_info handling); the per-op semantics inside the stub are a restatement, like the oracle's.
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+from oracle import postproc  # noqa: E402
+
+WIRING = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_net_wiring.npz"))
+WIRING_TAGS = sorted(k[:-4] for k in WIRING.files if k.endswith("_cfg"))
+
+
+def test_reference_graph_asks_for_exactly_the_variables_the_engine_requires():
+    from ctpn_b200.engine import REQUIRED_VARIABLES
+    assert sorted(REQUIRED_VARIABLES) == list(WIRING["variables_requested"]) and len(REQUIRED_VARIABLES) == 38
+    assert sorted(synth.make_weights(0)) == sorted(REQUIRED_VARIABLES)
+
+
+@pytest.mark.parametrize("tag", WIRING_TAGS)
+def test_oracle_matches_the_reference_graph_code_on_the_tf_stub(tag):
+    wseed = int(WIRING[tag + "_cfg"][0])
+    w = synth.make_weights(wseed)
+    names = {"conv1_1": "conv1_1", "conv1_2+pool": "pool1", "conv5_3": "conv5_3", "rpn_conv/3x3": "rpn_conv_3x3", "lstm_o": "lstm_o",
+             "rpn_cls_score": "rpn_cls_score", "rpn_bbox_pred": "rpn_bbox_pred", "rpn_cls_prob_reshape": "rpn_cls_prob_reshape"}
+    got = net_cpu.forward(WIRING[tag + "_blob"], w, taps=list(names))
+    for ours, theirs in names.items():
+        a, b = got[ours], WIRING["%s_%s" % (tag, theirs)]
+        if theirs in ("conv1_1", "pool1"):
+            a = a[:, ::5, ::5, :]                                     # the fixture keeps a strided sample of the large maps
+        assert a.shape == b.shape, (ours, a.shape, b.shape)
+        # float32 sums of up to 4608 products in two different orders: measured <= 3.1e-6 of the tensor's maximum
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(b).max()), (ours, float(np.abs(a - b).max()))
+    info = WIRING[tag + "_im_info"]
+    blob, _ = postproc.proposal_layer(got["rpn_cls_prob_reshape"], got["rpn_bbox_pred"], info, exp_mode="numpy")
+    scores, boxes = blob[:, 0], blob[:, 1:5] / info[0, 2]            # test.py:54-57
+    assert scores.shape == WIRING[tag + "_scores"].shape              # the same number of proposals survives, in the same order:
+    assert np.abs(scores - WIRING[tag + "_scores"]).max() <= 2e-5     # measured 4.4e-6
+    assert np.abs(boxes - WIRING[tag + "_boxes"]).max() <= 1e-3       # measured 1.2e-4 px

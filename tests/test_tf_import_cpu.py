@@ -134,7 +134,7 @@ def test_load_weight_file_dispatch(tmp_path):
     np.savez(str(tmp_path / "w.npz"), **w)
     for loc in (prefix, str(tmp_path), str(tmp_path / "g.pb"), str(tmp_path / "w.npz")):
         got = load_weight_file(loc)
-        assert sorted(got) == sorted(w), loc                                # exactly the 36 network variables
+        assert sorted(got) == sorted(w), loc                                # exactly the 38 network variables
         for k in w:
             np.testing.assert_array_equal(got[k], w[k])
     os.remove(prefix + ".index")

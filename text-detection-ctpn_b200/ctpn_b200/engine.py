@@ -535,7 +535,7 @@ class Engine:
         return self.detect_batch(image[None], im_scale)[0]
 
 
-# the 36 variables of the VGGnet_test graph; a TF checkpoint also holds optimizer slots etc.
+# the 38 variables of the VGGnet_test graph; a TF checkpoint also holds optimizer slots etc.
 REQUIRED_VARIABLES = tuple(
     ["%s/%s" % (l, k) for l in ("conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1",
                                 "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3", "rpn_conv/3x3")
@@ -551,7 +551,7 @@ def load_weight_file(path):
       * a frozen GraphDef `.pb` (ctpn/generate_pb.py:36-40, ctpn/demo_pb.py),
       * the VGG `.npy` dict (network.py:40-53: np.load(..., encoding='latin1').item() -> {layer: {'weights', 'biases'}}),
       * this repo's `.npz` with those variable names.
-    Checkpoints and graphs are reduced to the 36 network variables (a missing one raises KeyError)."""
+    Checkpoints and graphs are reduced to the 38 network variables (a missing one raises KeyError)."""
     from . import tf_import
     if path.endswith(".npz"):
         with np.load(path) as z:
