@@ -155,6 +155,8 @@ extern "C" int ctpn_anchor_targets_host(const double *gt_boxes, int num_gt, int 
   bool unmatched_gt = false;
   for (int k = 0; k < num_gt; ++k) unmatched_gt |= (gt_best[k] == 0.0);
 
+  std::vector<float> log_cache((size_t)num_gt * (kNumAnchors + 1));
+  std::vector<unsigned char> log_have((size_t)num_gt * (kNumAnchors + 1), 0);
   // pass 2: labels (:138-150) and regression targets against the best ground truth (:201, bbox_transform.py:10-29)
   for (int row = 0; row < feat_h; ++row)
     for (int col = 0; col < feat_w; ++col)
@@ -191,8 +193,14 @@ extern "C" int ctpn_anchor_targets_host(const double *gt_boxes, int num_gt, int 
         float *t = bbox_targets + 4 * i;
         t[0] = (float)((gt_cx - ex_cx) / ex_w);
         t[1] = (float)((gt_cy - ex_cy) / ex_h);
-        t[2] = (float)log(gt_w / ex_w);
-        t[3] = (float)log(gt_h / ex_h);
+        // the two logarithms depend on (ground truth, anchor shape) only -- every anchor is 16 wide and has one of 10
+        // heights -- so each distinct value is computed once instead of twice per anchor
+        float *cached = &log_cache[(size_t)best_gt[i] * (kNumAnchors + 1)];
+        unsigned char *have = &log_have[(size_t)best_gt[i] * (kNumAnchors + 1)];
+        if (!have[kNumAnchors]) cached[kNumAnchors] = (float)log(gt_w / ex_w), have[kNumAnchors] = 1;
+        if (!have[a]) cached[a] = (float)log(gt_h / ex_h), have[a] = 1;
+        t[2] = cached[kNumAnchors];
+        t[3] = cached[a];
       }
 
   // :153-160 dontcare areas: share of each anchor covered by them, summed area by area
