@@ -75,6 +75,13 @@ def test_oracle_matches_the_reference_graph_code_on_the_tf_stub(tag):
     info = WIRING[tag + "_im_info"]
     blob, _ = postproc.proposal_layer(got["rpn_cls_prob_reshape"], got["rpn_bbox_pred"], info, exp_mode="numpy")
     scores, boxes = blob[:, 0], blob[:, 1:5] / info[0, 2]            # test.py:54-57
-    assert scores.shape == WIRING[tag + "_scores"].shape              # the same number of proposals survives, in the same order:
-    assert np.abs(scores - WIRING[tag + "_scores"]).max() <= 2e-5     # measured 4.4e-6
-    assert np.abs(boxes - WIRING[tag + "_boxes"]).max() <= 1e-3       # measured 1.2e-4 px
+    want_s, want_b = WIRING[tag + "_scores"], WIRING[tag + "_boxes"]
+    # Here (same BLAS) the lists are equal row for row: same count, same order, scores within 4.4e-6, boxes within 1.2e-4 px.
+    # Asserted order-insensitively with a little slack, so that another float32 summation order (a different oneDNN / BLAS
+    # build) that swaps two near-equal scores or flips one NMS decision does not fail the wiring check.
+    assert abs(len(scores) - len(want_s)) <= 2
+    hit = 0
+    for s_ref, b_ref in zip(want_s, want_b):
+        close = np.abs(scores - s_ref) <= 2e-5
+        hit += bool(close.any()) and bool((np.abs(boxes[close] - b_ref).max(axis=1) <= 1e-3).any())
+    assert hit >= 0.98 * len(want_s), (hit, len(want_s))
